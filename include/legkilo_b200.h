@@ -184,6 +184,12 @@ int lk_init_process_cov(const lk_eskf_cfg* cfg, double* Q900);
 /* State::State() (eskf.cc:5-16). */
 int lk_state_default(lk_state* x);
 
+/* Pinned host memory for callers that want asynchronous H2D / D2H (cudaHostAlloc / cudaFreeHost). */
+int lk_host_alloc(void** p, size_t bytes);
+int lk_host_free(void* p);
+/* Tuning knobs by name (e.g. "gather_mode": 0 = per-thread vector loads, 1 = bulk-copy staging). */
+int lk_set_param(lk_handle h, const char* name, double value);
+
 /* ---- map ------------------------------------------------------------------------------- */
 
 /* Reserve device capacity for the map (root voxels, octree nodes, retained points). Optional:

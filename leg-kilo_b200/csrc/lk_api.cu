@@ -1,0 +1,671 @@
+// lk_api.cu — the extern "C" boundary (include/legkilo_b200.h): context, device memory,
+// staging, launch sequencing. No CPU fallback anywhere: without a CUDA device lk_create fails.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "lk_kernels.h"
+
+using namespace lk;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            if (e != cudaSuccess) return e;
+            want = bytes;
+        }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct lk_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    lk_eskf_cfg ec;
+    lk_map_cfg mc;
+    Globals g;
+    int gather_mode = 0;
+
+    // map
+    DevBuf slots, nodes, aux, points, roots_tmp, flag;
+    uint64_t hash_cap = 0;
+    uint32_t n_roots = 0, n_nodes = 0;
+    uint64_t n_points = 0;
+    uint64_t reserve_roots = 0, reserve_nodes = 0, reserve_points = 0;
+
+    // staged batch
+    int batch = 0;
+    uint64_t total_pts = 0;
+    uint32_t total_chunks = 0, n_steps = 0;
+    std::vector<uint32_t> step_chunk_ptr;
+    DevBuf pts, world, chunks, stepinit, x_in, P_in, clk_in, Q, x, P, clk, sc, step, partial, ticket, n_eff;
+    DevBuf dbg_ok, dbg_h, dbg_z, dbg_R, dbg_key, tmp;
+
+    // timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> kev;
+    float last_total_ms = 0, last_residual_ms = 0;
+    uint32_t last_launches = 0, last_residual_launches = 0;
+};
+
+namespace {
+
+int fail(lk_handle h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define LK_CUDA(h, expr)                                                                              \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess) {                                                                     \
+            cudaGetLastError();                                                                       \
+            return fail(h, e__ == cudaErrorMemoryAllocation ? LK_ERR_OUT_OF_MEMORY : LK_ERR_CUDA,      \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                         \
+        }                                                                                             \
+    } while (0)
+
+uint64_t next_pow2(uint64_t v) {
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+void fill_globals(lk_context* c, const double* extR, const double* extT) {
+    Globals& g = c->g;
+    for (int i = 0; i < 9; ++i) g.Re[i] = extR[i];
+    for (int i = 0; i < 3; ++i) g.te[i] = extT[i];
+    g.voxel = c->mc.max_voxel_size;
+    int ex = 0;
+    double m = std::frexp(g.voxel, &ex);
+    g.voxel_pow2 = (m == 0.5 && g.voxel > 0) ? 1 : 0;
+    g.inv_voxel = 1.0 / g.voxel;
+    g.sigma_num = c->mc.sigma_num;
+    g.ratio = c->ec.lidar_point_meas_ratio;
+    // calcBodyCov(pb, dept_err (float range_inc), beam_err (float degree_inc)) — voxel_map.cc:22-27
+    float range_inc = (float)c->mc.dept_err;
+    float degree_inc = (float)c->mc.beam_err;
+    g.rv = range_inc * range_inc;
+    double sd = std::sin((double)degree_inc * 0.017453293);  // PCL DEG2RAD
+    g.dv = sd * sd;
+    g.voxel_f = (float)c->mc.max_voxel_size;
+    g.planer_threshold = (float)c->mc.planner_threshold;
+    g.max_layer = c->mc.max_layer;
+    g.max_points_num = c->mc.max_points_num;
+    for (int i = 0; i < 5; ++i) g.layer_init_num[i] = c->mc.layer_init_num[i];
+}
+
+int ensure_hash(lk_context* c, uint64_t n_roots_wanted) {
+    uint64_t want = next_pow2(std::max<uint64_t>(1024, 2 * std::max(n_roots_wanted, c->reserve_roots)));
+    if (want > (1ull << 31)) return fail(c, LK_ERR_CAPACITY, "root table too large");
+    if (want != c->hash_cap) {
+        LK_CUDA(c, c->slots.ensure(want * sizeof(HashSlot)));
+        c->hash_cap = want;
+    }
+    launch_hash_clear(c->slots.as<HashSlot>(), c->hash_cap, c->stream);
+    LK_CUDA(c, cudaGetLastError());
+    return LK_OK;
+}
+
+uint32_t chunk_size_for(uint32_t n) {
+    // a function of the bucket alone, so results are bitwise independent of how a batch is
+    // sharded across GPUs (SURVEY §4 multi-GPU invariant)
+    uint32_t c = (n + 63) / 64;
+    c = ((c + 255) / 256) * 256;
+    if (c < 256) c = 256;
+    if (c > 4096) c = 4096;
+    return c;
+}
+
+cudaEvent_t kev_get(lk_context* c, size_t i) {
+    while (c->kev.size() <= i) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->kev.push_back(e);
+    }
+    return c->kev[i];
+}
+
+ResidualArgs residual_args(lk_context* c) {
+    ResidualArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.pts = c->pts.as<float4>();
+    a.slots = c->slots.as<HashSlot>();
+    a.hash_mask = (uint32_t)(c->hash_cap - 1);
+    a.nodes = c->nodes.as<MapNode>();
+    a.chunks = c->chunks.as<ChunkDesc>();
+    a.sc = c->sc.as<ScanConst>();
+    a.step = c->step.as<ScanStep>();
+    a.partial = c->partial.as<double>();
+    a.ticket = c->ticket.as<uint32_t>();
+    a.x = c->x.as<double>();
+    a.P = c->P.as<double>();
+    a.clk = c->clk.as<lk_stream_clock>();
+    a.n_eff = c->n_eff.as<uint32_t>();
+    a.g = c->g;
+    return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lk_abi_version(void) { return LK_ABI_VERSION; }
+
+const char* lk_last_error(lk_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int lk_create(const lk_eskf_cfg* eskf_cfg, const lk_map_cfg* map_cfg, const double ext_rot[9], const double ext_t[3],
+              int device, lk_handle* out) {
+    if (!eskf_cfg || !map_cfg || !ext_rot || !ext_t || !out) return fail(nullptr, LK_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, LK_ERR_NO_DEVICE,
+                    std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count == 0") +
+                        " (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail(nullptr, LK_ERR_INVALID_ARG, "device ordinal out of range");
+    if (map_cfg->max_layer < 0 || map_cfg->max_layer > 4) return fail(nullptr, LK_ERR_INVALID_ARG, "max_layer must be 0..4");
+    if (!(map_cfg->max_voxel_size > 0)) return fail(nullptr, LK_ERR_INVALID_ARG, "voxel size must be positive");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, LK_ERR_CUDA, cudaGetErrorString(e));
+    lk_context* c = new lk_context;
+    c->device = device;
+    c->ec = *eskf_cfg;
+    c->mc = *map_cfg;
+    fill_globals(c, ext_rot, ext_t);
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(nullptr, LK_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    *out = c;
+    return LK_OK;
+}
+
+int lk_destroy(lk_handle h) {
+    if (!h) return LK_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->slots, &h->nodes, &h->aux, &h->points, &h->roots_tmp, &h->flag, &h->pts, &h->world,
+                      &h->chunks, &h->stepinit, &h->x_in, &h->P_in, &h->clk_in, &h->Q, &h->x, &h->P, &h->clk, &h->sc,
+                      &h->step, &h->partial, &h->ticket, &h->n_eff, &h->dbg_ok, &h->dbg_h, &h->dbg_z, &h->dbg_R,
+                      &h->dbg_key, &h->tmp};
+    for (DevBuf* b : bufs) b->release();
+    for (cudaEvent_t e : h->kev) cudaEventDestroy(e);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return LK_OK;
+}
+
+int lk_init_process_cov(const lk_eskf_cfg* c, double* Q) {
+    if (!c || !Q) return LK_ERR_INVALID_ARG;
+    for (int i = 0; i < 900; ++i) Q[i] = 0.0;
+    const double d[7] = {c->vel_process_cov,     c->acc_bias_process_cov, c->gyr_bias_process_cov, c->imu_acc_process_cov,
+                         c->imu_gyr_process_cov, c->kin_bias_process_cov, c->contact_process_cov};
+    const int at[7] = {6, 9, 12, 18, 21, 24, 27};
+    for (int b = 0; b < 7; ++b)
+        for (int k = 0; k < 3; ++k) Q[(at[b] + k) * 30 + at[b] + k] = d[b];
+    return LK_OK;
+}
+
+int lk_state_default(lk_state* x) {
+    if (!x) return LK_ERR_INVALID_ARG;
+    std::memset(x, 0, sizeof(*x));
+    x->rot[0] = x->rot[4] = x->rot[8] = 1.0;
+    x->grav[2] = -9.81;
+    return LK_OK;
+}
+
+int lk_host_alloc(void** p, size_t bytes) {
+    if (!p) return LK_ERR_INVALID_ARG;
+    cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return LK_ERR_OUT_OF_MEMORY;
+    }
+    return LK_OK;
+}
+
+int lk_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+    return LK_OK;
+}
+
+int lk_set_param(lk_handle h, const char* name, double value) {
+    if (!h || !name) return LK_ERR_INVALID_ARG;
+    if (!std::strcmp(name, "gather_mode")) { h->gather_mode = (int)value; return LK_OK; }
+    return fail(h, LK_ERR_INVALID_ARG, std::string("unknown parameter ") + name);
+}
+
+int lk_sync(lk_handle h) {
+    if (!h) return LK_ERR_INVALID_ARG;
+    cudaSetDevice(h->device);
+    LK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return LK_OK;
+}
+
+// ---- map ------------------------------------------------------------------------------------
+
+int lk_map_reserve(lk_handle h, uint64_t max_roots, uint64_t max_nodes, uint64_t max_points) {
+    if (!h) return LK_ERR_INVALID_ARG;
+    h->reserve_roots = max_roots;
+    h->reserve_nodes = max_nodes;
+    h->reserve_points = max_points;
+    return LK_OK;
+}
+
+int lk_map_upload(lk_handle h, const void* blob, size_t bytes) {
+    if (!h || !blob) return fail(h, LK_ERR_INVALID_ARG, "null argument");
+    cudaSetDevice(h->device);
+    if (bytes < sizeof(lk_map_blob_header)) return fail(h, LK_ERR_BAD_BLOB, "blob shorter than its header");
+    lk_map_blob_header hd;
+    std::memcpy(&hd, blob, sizeof(hd));
+    if (hd.magic != LK_MAP_MAGIC || hd.version != 1) return fail(h, LK_ERR_BAD_BLOB, "bad magic / version");
+    size_t need = sizeof(hd) + (size_t)hd.n_roots * sizeof(lk_map_root) + (size_t)hd.n_nodes * sizeof(lk_map_node) +
+                  (size_t)hd.n_nodes * sizeof(lk_map_aux) + (size_t)hd.n_points * sizeof(lk_map_point);
+    if (bytes < need) return fail(h, LK_ERR_BAD_BLOB, "blob truncated");
+    const char* p = (const char*)blob + sizeof(hd);
+    const lk_map_root* roots = (const lk_map_root*)p;
+    p += (size_t)hd.n_roots * sizeof(lk_map_root);
+    const lk_map_node* nodes = (const lk_map_node*)p;
+    p += (size_t)hd.n_nodes * sizeof(lk_map_node);
+    const lk_map_aux* aux = (const lk_map_aux*)p;
+    p += (size_t)hd.n_nodes * sizeof(lk_map_aux);
+    const lk_map_point* pts = (const lk_map_point*)p;
+    for (uint32_t r = 0; r < hd.n_roots; ++r)
+        if (roots[r].node < 0 || (uint32_t)roots[r].node >= hd.n_nodes) return fail(h, LK_ERR_BAD_BLOB, "root node index out of range");
+
+    int rc = ensure_hash(h, hd.n_roots);
+    if (rc) return rc;
+    size_t node_cap = std::max<uint64_t>(hd.n_nodes, h->reserve_nodes);
+    size_t point_cap = std::max<uint64_t>(hd.n_points, h->reserve_points);
+    LK_CUDA(h, h->nodes.ensure(std::max<size_t>(node_cap, 1) * sizeof(MapNode)));
+    LK_CUDA(h, h->aux.ensure(std::max<size_t>(node_cap, 1) * sizeof(MapAux)));
+    LK_CUDA(h, h->points.ensure(std::max<size_t>(point_cap, 1) * sizeof(MapPoint)));
+    LK_CUDA(h, h->roots_tmp.ensure(std::max<size_t>(hd.n_roots, 1) * sizeof(lk_map_root)));
+    LK_CUDA(h, h->flag.ensure(64));
+    LK_CUDA(h, cudaMemcpyAsync(h->nodes.p, nodes, (size_t)hd.n_nodes * sizeof(MapNode), cudaMemcpyHostToDevice, h->stream));
+    LK_CUDA(h, cudaMemcpyAsync(h->aux.p, aux, (size_t)hd.n_nodes * sizeof(MapAux), cudaMemcpyHostToDevice, h->stream));
+    LK_CUDA(h, cudaMemcpyAsync(h->points.p, pts, (size_t)hd.n_points * sizeof(MapPoint), cudaMemcpyHostToDevice, h->stream));
+    LK_CUDA(h, cudaMemcpyAsync(h->roots_tmp.p, roots, (size_t)hd.n_roots * sizeof(lk_map_root), cudaMemcpyHostToDevice, h->stream));
+    LK_CUDA(h, cudaMemsetAsync(h->flag.p, 0, 64, h->stream));
+    launch_hash_insert_roots(h->slots.as<HashSlot>(), (uint32_t)(h->hash_cap - 1), h->roots_tmp.as<lk_map_root>(),
+                             hd.n_roots, h->flag.as<uint32_t>(), h->stream);
+    LK_CUDA(h, cudaGetLastError());
+    uint32_t failed = 0;
+    LK_CUDA(h, cudaMemcpyAsync(&failed, h->flag.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    LK_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (failed) return fail(h, LK_ERR_CAPACITY, "root table overflow");
+    h->n_roots = hd.n_roots;
+    h->n_nodes = hd.n_nodes;
+    h->n_points = hd.n_points;
+    return LK_OK;
+}
+
+int lk_map_stats(lk_handle h, uint64_t out[4]) {
+    if (!h || !out) return LK_ERR_INVALID_ARG;
+    out[0] = h->n_roots;
+    out[1] = h->n_nodes;
+    out[2] = h->n_points;
+    out[3] = 0;
+    return LK_OK;
+}
+
+int lk_map_download(lk_handle h, void* blob, size_t capacity, size_t* bytes_out) {
+    if (!h) return LK_ERR_INVALID_ARG;
+    cudaSetDevice(h->device);
+    size_t need = sizeof(lk_map_blob_header) + (size_t)h->n_roots * sizeof(lk_map_root) +
+                  (size_t)h->n_nodes * (sizeof(lk_map_node) + sizeof(lk_map_aux)) + (size_t)h->n_points * sizeof(lk_map_point);
+    if (bytes_out) *bytes_out = need;
+    if (!blob) return LK_OK;
+    if (capacity < need) return fail(h, LK_ERR_CAPACITY, "blob buffer too small");
+    lk_map_blob_header hd;
+    std::memset(&hd, 0, sizeof(hd));
+    hd.magic = LK_MAP_MAGIC;
+    hd.version = 1;
+    hd.n_roots = h->n_roots;
+    hd.n_nodes = h->n_nodes;
+    hd.n_points = h->n_points;
+    char* p = (char*)blob;
+    std::memcpy(p, &hd, sizeof(hd));
+    p += sizeof(hd);
+    LK_CUDA(h, h->roots_tmp.ensure(std::max<size_t>(h->n_roots, 1) * sizeof(lk_map_root)));
+    LK_CUDA(h, h->flag.ensure(64));
+    LK_CUDA(h, cudaMemsetAsync(h->flag.p, 0, 64, h->stream));
+    if (h->hash_cap) launch_hash_dump_roots(h->slots.as<HashSlot>(), h->hash_cap, h->roots_tmp.as<lk_map_root>(),
+                                            h->flag.as<uint32_t>(), h->stream);
+    LK_CUDA(h, cudaGetLastError());
+    LK_CUDA(h, cudaMemcpyAsync(p, h->roots_tmp.p, (size_t)h->n_roots * sizeof(lk_map_root), cudaMemcpyDeviceToHost, h->stream));
+    p += (size_t)h->n_roots * sizeof(lk_map_root);
+    LK_CUDA(h, cudaMemcpyAsync(p, h->nodes.p, (size_t)h->n_nodes * sizeof(MapNode), cudaMemcpyDeviceToHost, h->stream));
+    p += (size_t)h->n_nodes * sizeof(MapNode);
+    LK_CUDA(h, cudaMemcpyAsync(p, h->aux.p, (size_t)h->n_nodes * sizeof(MapAux), cudaMemcpyDeviceToHost, h->stream));
+    p += (size_t)h->n_nodes * sizeof(MapAux);
+    LK_CUDA(h, cudaMemcpyAsync(p, h->points.p, (size_t)h->n_points * sizeof(MapPoint), cudaMemcpyDeviceToHost, h->stream));
+    LK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return LK_OK;
+}
+
+int lk_map_build(lk_handle h, const float*, const float*, size_t, const double*, const double*, const double*) {
+    return fail(h, LK_ERR_NOT_READY, "lk_map_build: device-side BuildVoxelMap not available in this build");
+}
+
+// ---- batch staging / run / fetch ----------------------------------------------------------------
+
+int lk_batch_stage(lk_handle h, int batch, const lk_state* x, const double* P, const double* Q,
+                   const lk_stream_clock* clk, const float* pts, const uint32_t* scan_offsets,
+                   const uint32_t* scan_bucket_ptr, const uint32_t* bucket_offsets, const double* bucket_times) {
+    if (!h) return LK_ERR_INVALID_ARG;
+    if (batch <= 0 || !x || !P || !Q || !clk || !scan_offsets || !scan_bucket_ptr || !bucket_offsets || !bucket_times)
+        return fail(h, LK_ERR_INVALID_ARG, "null / empty batch argument");
+    cudaSetDevice(h->device);
+    const uint64_t total = scan_offsets[batch];
+    if (total && !pts) return fail(h, LK_ERR_INVALID_ARG, "pts is null");
+    // host-side tables: chunks grouped by step (bucket rank inside its scan)
+    uint32_t max_buckets = 0;
+    for (int s = 0; s < batch; ++s) {
+        if (scan_offsets[s + 1] < scan_offsets[s]) return fail(h, LK_ERR_INVALID_ARG, "scan_offsets not monotone");
+        uint32_t nb = scan_bucket_ptr[s + 1] - scan_bucket_ptr[s];
+        max_buckets = std::max(max_buckets, nb);
+        for (uint32_t b = scan_bucket_ptr[s]; b < scan_bucket_ptr[s + 1]; ++b) {
+            if (bucket_offsets[b + 1] < bucket_offsets[b] || bucket_offsets[b] < scan_offsets[s] ||
+                bucket_offsets[b + 1] > scan_offsets[s + 1])
+                return fail(h, LK_ERR_INVALID_ARG, "bucket_offsets outside their scan");
+        }
+    }
+    std::vector<ChunkDesc> chunks;
+    std::vector<StepInit> inits((size_t)max_buckets * batch);
+    h->step_chunk_ptr.assign(max_buckets + 1, 0);
+    for (uint32_t k = 0; k < max_buckets; ++k) {
+        h->step_chunk_ptr[k] = (uint32_t)chunks.size();
+        for (int s = 0; s < batch; ++s) {
+            StepInit& in = inits[(size_t)k * batch + s];
+            std::memset(&in, 0, sizeof(in));
+            uint32_t nb = scan_bucket_ptr[s + 1] - scan_bucket_ptr[s];
+            if (k >= nb) continue;
+            uint32_t b = scan_bucket_ptr[s] + k;
+            uint32_t p0 = bucket_offsets[b], p1 = bucket_offsets[b + 1];
+            in.active = 1;
+            in.pt_begin = p0;
+            in.pt_end = p1;
+            in.t_bucket = bucket_times[b];
+            in.chunk_begin = (uint32_t)chunks.size();
+            uint32_t cs = chunk_size_for(p1 - p0);
+            for (uint32_t q = p0; q < p1; q += cs) {
+                ChunkDesc cd;
+                cd.scan = (uint32_t)s;
+                cd.start = q;
+                cd.count = std::min(cs, p1 - q);
+                cd.pad = 0;
+                chunks.push_back(cd);
+            }
+            in.chunk_end = (uint32_t)chunks.size();
+        }
+    }
+    h->step_chunk_ptr[max_buckets] = (uint32_t)chunks.size();
+    h->batch = batch;
+    h->total_pts = total;
+    h->total_chunks = (uint32_t)chunks.size();
+    h->n_steps = max_buckets;
+
+    LK_CUDA(h, h->pts.ensure(std::max<size_t>(total, 1) * 16));
+    LK_CUDA(h, h->world.ensure(std::max<size_t>(total, 1) * 16));
+    LK_CUDA(h, h->chunks.ensure(std::max<size_t>(chunks.size(), 1) * sizeof(ChunkDesc)));
+    LK_CUDA(h, h->stepinit.ensure(std::max<size_t>(inits.size(), 1) * sizeof(StepInit)));
+    LK_CUDA(h, h->x_in.ensure((size_t)batch * sizeof(lk_state)));
+    LK_CUDA(h, h->P_in.ensure((size_t)batch * 900 * 8));
+    LK_CUDA(h, h->clk_in.ensure((size_t)batch * sizeof(lk_stream_clock)));
+    LK_CUDA(h, h->Q.ensure(900 * 8));
+    LK_CUDA(h, h->x.ensure((size_t)batch * sizeof(lk_state)));
+    LK_CUDA(h, h->P.ensure((size_t)batch * 900 * 8));
+    LK_CUDA(h, h->clk.ensure((size_t)batch * sizeof(lk_stream_clock)));
+    LK_CUDA(h, h->sc.ensure((size_t)batch * sizeof(ScanConst)));
+    LK_CUDA(h, h->step.ensure((size_t)batch * sizeof(ScanStep)));
+    LK_CUDA(h, h->partial.ensure(std::max<size_t>(chunks.size(), 1) * PARTIAL_STRIDE * 8));
+    LK_CUDA(h, h->ticket.ensure((size_t)batch * 4));
+    LK_CUDA(h, h->n_eff.ensure((size_t)batch * 4));
+    cudaStream_t s = h->stream;
+    if (total) LK_CUDA(h, cudaMemcpyAsync(h->pts.p, pts, total * 16, cudaMemcpyHostToDevice, s));
+    if (!chunks.empty()) LK_CUDA(h, cudaMemcpyAsync(h->chunks.p, chunks.data(), chunks.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice, s));
+    if (!inits.empty()) LK_CUDA(h, cudaMemcpyAsync(h->stepinit.p, inits.data(), inits.size() * sizeof(StepInit), cudaMemcpyHostToDevice, s));
+    LK_CUDA(h, cudaMemcpyAsync(h->x_in.p, x, (size_t)batch * sizeof(lk_state), cudaMemcpyHostToDevice, s));
+    LK_CUDA(h, cudaMemcpyAsync(h->P_in.p, P, (size_t)batch * 900 * 8, cudaMemcpyHostToDevice, s));
+    LK_CUDA(h, cudaMemcpyAsync(h->clk_in.p, clk, (size_t)batch * sizeof(lk_stream_clock), cudaMemcpyHostToDevice, s));
+    LK_CUDA(h, cudaMemcpyAsync(h->Q.p, Q, 900 * 8, cudaMemcpyHostToDevice, s));
+    LK_CUDA(h, cudaStreamSynchronize(s));  // the host tables above go out of scope
+    return LK_OK;
+}
+
+int lk_batch_run(lk_handle h, int iters, int update_map) {
+    if (!h) return LK_ERR_INVALID_ARG;
+    if (h->batch <= 0) return fail(h, LK_ERR_NOT_READY, "lk_batch_run before lk_batch_stage");
+    if (iters < 1) return fail(h, LK_ERR_INVALID_ARG, "iters must be >= 1");
+    if (update_map) return fail(h, LK_ERR_NOT_READY, "update_map: device-side UpdateVoxelMap not available in this build");
+    if (!h->hash_cap) return fail(h, LK_ERR_NOT_READY, "no map: call lk_map_upload or lk_map_build first");
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    const int batch = h->batch;
+    LK_CUDA(h, cudaEventRecord(h->ev0, s));
+    LK_CUDA(h, cudaMemcpyAsync(h->x.p, h->x_in.p, (size_t)batch * sizeof(lk_state), cudaMemcpyDeviceToDevice, s));
+    LK_CUDA(h, cudaMemcpyAsync(h->P.p, h->P_in.p, (size_t)batch * 900 * 8, cudaMemcpyDeviceToDevice, s));
+    LK_CUDA(h, cudaMemcpyAsync(h->clk.p, h->clk_in.p, (size_t)batch * sizeof(lk_stream_clock), cudaMemcpyDeviceToDevice, s));
+    LK_CUDA(h, cudaMemsetAsync(h->n_eff.p, 0, (size_t)batch * 4, s));
+    uint32_t launches = 0, rlaunches = 0;
+    size_t nev = 0;
+    for (uint32_t k = 0; k < h->n_steps; ++k) {
+        PredictArgs pa;
+        pa.init = h->stepinit.as<StepInit>() + (size_t)k * batch;
+        pa.step = h->step.as<ScanStep>();
+        pa.sc = h->sc.as<ScanConst>();
+        pa.x = h->x.as<double>();
+        pa.P = h->P.as<double>();
+        pa.Q = h->Q.as<double>();
+        pa.clk = h->clk.as<lk_stream_clock>();
+        pa.ticket = h->ticket.as<uint32_t>();
+        pa.batch = batch;
+        launch_predict_prepare(pa, s);
+        ++launches;
+        uint32_t c0 = h->step_chunk_ptr[k], c1 = h->step_chunk_ptr[k + 1];
+        for (int it = 0; it < iters; ++it) {
+            ResidualArgs ra = residual_args(h);
+            ra.chunk_first = c0;
+            ra.last_iter = (it == iters - 1) ? 1 : 0;
+            cudaEvent_t e0 = kev_get(h, nev++), e1 = kev_get(h, nev++);
+            cudaEventRecord(e0, s);
+            launch_residual(ra, c1 - c0, false, h->gather_mode, s);
+            cudaEventRecord(e1, s);
+            if (c1 > c0) { ++launches; ++rlaunches; }
+        }
+        ReprojectArgs rp;
+        rp.pts = h->pts.as<float4>();
+        rp.world = h->world.as<float4>();
+        rp.chunks = h->chunks.as<ChunkDesc>();
+        rp.chunk_first = c0;
+        rp.sc = h->sc.as<ScanConst>();
+        rp.step = h->step.as<ScanStep>();
+        rp.g = h->g;
+        launch_reproject(rp, c1 - c0, s);
+        if (c1 > c0) ++launches;
+    }
+    LK_CUDA(h, cudaGetLastError());
+    LK_CUDA(h, cudaEventRecord(h->ev1, s));
+    LK_CUDA(h, cudaStreamSynchronize(s));
+    LK_CUDA(h, cudaEventElapsedTime(&h->last_total_ms, h->ev0, h->ev1));
+    float rms = 0;
+    for (size_t i = 0; i + 1 < nev; i += 2) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->kev[i], h->kev[i + 1]);
+        rms += ms;
+    }
+    h->last_residual_ms = rms;
+    h->last_launches = launches;
+    h->last_residual_launches = rlaunches;
+    return LK_OK;
+}
+
+int lk_batch_fetch(lk_handle h, lk_state* x_out, double* P_out, lk_stream_clock* clk_out, float* pts_world_out,
+                   uint32_t* n_effective_out) {
+    if (!h) return LK_ERR_INVALID_ARG;
+    if (h->batch <= 0) return fail(h, LK_ERR_NOT_READY, "nothing staged");
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    const int batch = h->batch;
+    if (x_out) LK_CUDA(h, cudaMemcpyAsync(x_out, h->x.p, (size_t)batch * sizeof(lk_state), cudaMemcpyDeviceToHost, s));
+    if (P_out) LK_CUDA(h, cudaMemcpyAsync(P_out, h->P.p, (size_t)batch * 900 * 8, cudaMemcpyDeviceToHost, s));
+    if (clk_out) LK_CUDA(h, cudaMemcpyAsync(clk_out, h->clk.p, (size_t)batch * sizeof(lk_stream_clock), cudaMemcpyDeviceToHost, s));
+    if (pts_world_out && h->total_pts)
+        LK_CUDA(h, cudaMemcpyAsync(pts_world_out, h->world.p, h->total_pts * 16, cudaMemcpyDeviceToHost, s));
+    if (n_effective_out) LK_CUDA(h, cudaMemcpyAsync(n_effective_out, h->n_eff.p, (size_t)batch * 4, cudaMemcpyDeviceToHost, s));
+    LK_CUDA(h, cudaStreamSynchronize(s));
+    return LK_OK;
+}
+
+int lk_batch_last_timing(lk_handle h, float* total_ms, float* residual_kernel_ms, uint32_t* n_kernel_launches,
+                         uint32_t* n_residual_launches) {
+    if (!h) return LK_ERR_INVALID_ARG;
+    if (total_ms) *total_ms = h->last_total_ms;
+    if (residual_kernel_ms) *residual_kernel_ms = h->last_residual_ms;
+    if (n_kernel_launches) *n_kernel_launches = h->last_launches;
+    if (n_residual_launches) *n_residual_launches = h->last_residual_launches;
+    return LK_OK;
+}
+
+int lk_scan_update(lk_handle h, int batch, lk_state* x_inout, double* P_inout, const double* Q,
+                   lk_stream_clock* clk_inout, const float* pts, const uint32_t* scan_offsets,
+                   const uint32_t* scan_bucket_ptr, const uint32_t* bucket_offsets, const double* bucket_times, int iters,
+                   int update_map, float* pts_world_out, uint32_t* n_effective_out) {
+    int rc = lk_batch_stage(h, batch, x_inout, P_inout, Q, clk_inout, pts, scan_offsets, scan_bucket_ptr, bucket_offsets,
+                            bucket_times);
+    if (rc) return rc;
+    rc = lk_batch_run(h, iters, update_map);
+    if (rc) return rc;
+    return lk_batch_fetch(h, x_inout, P_inout, clk_inout, pts_world_out, n_effective_out);
+}
+
+int lk_debug_residuals(lk_handle h, const lk_state* x, const double* P, const float* pts, uint32_t n, uint8_t* ok_out,
+                       double* h_out, double* z_out, double* R_out, int32_t* key_out) {
+    if (!h || !x || !P || (!pts && n)) return fail(h, LK_ERR_INVALID_ARG, "null argument");
+    if (!h->hash_cap) return fail(h, LK_ERR_NOT_READY, "no map");
+    std::vector<double> Q(900, 0.0);
+    lk_stream_clock clk = {0.0, 0.0};
+    uint32_t so[2] = {0, n}, sb[2] = {0, 1}, bo[2] = {0, n};
+    double bt[1] = {0.0};
+    int rc = lk_batch_stage(h, 1, x, P, Q.data(), &clk, pts, so, sb, bo, bt);
+    if (rc) return rc;
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    size_t nn = std::max<size_t>(n, 1);
+    LK_CUDA(h, h->dbg_ok.ensure(nn));
+    LK_CUDA(h, h->dbg_h.ensure(nn * 48));
+    LK_CUDA(h, h->dbg_z.ensure(nn * 8));
+    LK_CUDA(h, h->dbg_R.ensure(nn * 8));
+    LK_CUDA(h, h->dbg_key.ensure(nn * 12));
+    LK_CUDA(h, cudaMemcpyAsync(h->x.p, h->x_in.p, sizeof(lk_state), cudaMemcpyDeviceToDevice, s));
+    LK_CUDA(h, cudaMemcpyAsync(h->P.p, h->P_in.p, 900 * 8, cudaMemcpyDeviceToDevice, s));
+    LK_CUDA(h, cudaMemcpyAsync(h->clk.p, h->clk_in.p, sizeof(lk_stream_clock), cudaMemcpyDeviceToDevice, s));
+    PredictArgs pa;
+    pa.init = h->stepinit.as<StepInit>();
+    pa.step = h->step.as<ScanStep>();
+    pa.sc = h->sc.as<ScanConst>();
+    pa.x = h->x.as<double>();
+    pa.P = h->P.as<double>();
+    pa.Q = h->Q.as<double>();
+    pa.clk = h->clk.as<lk_stream_clock>();
+    pa.ticket = h->ticket.as<uint32_t>();
+    pa.batch = 1;
+    launch_predict_prepare(pa, s);
+    ResidualArgs ra = residual_args(h);
+    ra.chunk_first = 0;
+    ra.dbg_ok = h->dbg_ok.as<uint8_t>();
+    ra.dbg_h = h->dbg_h.as<double>();
+    ra.dbg_z = h->dbg_z.as<double>();
+    ra.dbg_R = h->dbg_R.as<double>();
+    ra.dbg_key = h->dbg_key.as<int32_t>();
+    launch_residual(ra, h->total_chunks, true, 0, s);
+    LK_CUDA(h, cudaGetLastError());
+    if (n) {
+        if (ok_out) LK_CUDA(h, cudaMemcpyAsync(ok_out, h->dbg_ok.p, n, cudaMemcpyDeviceToHost, s));
+        if (h_out) LK_CUDA(h, cudaMemcpyAsync(h_out, h->dbg_h.p, (size_t)n * 48, cudaMemcpyDeviceToHost, s));
+        if (z_out) LK_CUDA(h, cudaMemcpyAsync(z_out, h->dbg_z.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        if (R_out) LK_CUDA(h, cudaMemcpyAsync(R_out, h->dbg_R.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        if (key_out) LK_CUDA(h, cudaMemcpyAsync(key_out, h->dbg_key.p, (size_t)n * 12, cudaMemcpyDeviceToHost, s));
+    }
+    LK_CUDA(h, cudaStreamSynchronize(s));
+    return LK_OK;
+}
+
+// ---- filter steps ---------------------------------------------------------------------------------
+
+int lk_predict(lk_handle h, int batch, lk_state* x_inout, double* P_inout, const double* Q, const double* dt,
+               int prop_state, int prop_cov) {
+    if (!h || batch <= 0 || !x_inout || !P_inout || !Q || !dt) return fail(h, LK_ERR_INVALID_ARG, "null argument");
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    LK_CUDA(h, h->x.ensure((size_t)batch * sizeof(lk_state)));
+    LK_CUDA(h, h->P.ensure((size_t)batch * 900 * 8));
+    LK_CUDA(h, h->Q.ensure(900 * 8));
+    LK_CUDA(h, h->tmp.ensure((size_t)batch * 8));
+    LK_CUDA(h, cudaMemcpyAsync(h->x.p, x_inout, (size_t)batch * sizeof(lk_state), cudaMemcpyHostToDevice, s));
+    LK_CUDA(h, cudaMemcpyAsync(h->P.p, P_inout, (size_t)batch * 900 * 8, cudaMemcpyHostToDevice, s));
+    LK_CUDA(h, cudaMemcpyAsync(h->Q.p, Q, 900 * 8, cudaMemcpyHostToDevice, s));
+    LK_CUDA(h, cudaMemcpyAsync(h->tmp.p, dt, (size_t)batch * 8, cudaMemcpyHostToDevice, s));
+    launch_predict_dt(h->x.as<double>(), h->P.as<double>(), h->Q.as<double>(), h->tmp.as<double>(), batch, prop_state,
+                      prop_cov, s);
+    LK_CUDA(h, cudaGetLastError());
+    LK_CUDA(h, cudaMemcpyAsync(x_inout, h->x.p, (size_t)batch * sizeof(lk_state), cudaMemcpyDeviceToHost, s));
+    LK_CUDA(h, cudaMemcpyAsync(P_inout, h->P.p, (size_t)batch * 900 * 8, cudaMemcpyDeviceToHost, s));
+    LK_CUDA(h, cudaStreamSynchronize(s));
+    return LK_OK;
+}
+
+int lk_update_by_points(lk_handle h, lk_state*, double*, uint32_t, const double*, const double*, const double*) {
+    return fail(h, LK_ERR_NOT_READY, "lk_update_by_points not available in this build");
+}
+int lk_obs_imu(lk_handle h, lk_state*, double*, const double*, lk_stream_clock*, const lk_imu_meas*, uint32_t, double, double) {
+    return fail(h, LK_ERR_NOT_READY, "lk_obs_imu not available in this build");
+}
+int lk_obs_kinimu(lk_handle h, lk_state*, double*, const double*, lk_stream_clock*, const lk_kinimu_meas*, uint32_t, double,
+                  double) {
+    return fail(h, LK_ERR_NOT_READY, "lk_obs_kinimu not available in this build");
+}
+int lk_process_scan(lk_handle h, lk_state*, double*, const double*, lk_stream_clock*, const float*, uint32_t, const uint32_t*,
+                    const double*, uint32_t, const lk_imu_meas*, const lk_kinimu_meas*, uint32_t, double, double, int, int,
+                    float*, uint32_t*, uint32_t*) {
+    return fail(h, LK_ERR_NOT_READY, "lk_process_scan not available in this build");
+}
+
+}  // extern "C"
