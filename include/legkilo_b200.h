@@ -190,6 +190,9 @@ int lk_host_free(void* p);
 /* Tuning knobs by name (e.g. "gather_mode": 0 = per-thread vector loads, 1 = bulk-copy staging). */
 int lk_set_param(lk_handle h, const char* name, double value);
 
+/* Debug read-back of internal device buffers (what: 0 = per-chunk partial sums, 1 = scan constants). */
+int lk_debug_read(lk_handle h, int what, void* dst, size_t bytes);
+
 /* ---- map ------------------------------------------------------------------------------- */
 
 /* Reserve device capacity for the map (root voxels, octree nodes, retained points). Optional:

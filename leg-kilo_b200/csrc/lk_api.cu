@@ -271,6 +271,16 @@ int lk_set_param(lk_handle h, const char* name, double value) {
     return fail(h, LK_ERR_INVALID_ARG, std::string("unknown parameter ") + name);
 }
 
+// Debug read-back of internal device buffers: what = 0 partial sums, 1 scan constants.
+int lk_debug_read(lk_handle h, int what, void* dst, size_t bytes) {
+    if (!h || !dst) return LK_ERR_INVALID_ARG;
+    cudaSetDevice(h->device);
+    DevBuf* b = what == 0 ? &h->partial : &h->sc;
+    if (bytes > b->cap) bytes = b->cap;
+    LK_CUDA(h, cudaMemcpy(dst, b->p, bytes, cudaMemcpyDeviceToHost));
+    return LK_OK;
+}
+
 int lk_sync(lk_handle h) {
     if (!h) return LK_ERR_INVALID_ARG;
     cudaSetDevice(h->device);

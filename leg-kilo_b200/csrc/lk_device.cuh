@@ -57,7 +57,8 @@ struct ScanConst {
 };
 
 // 32 doubles per chunk partial: A upper (21) | b (6) | sumR | count | pad
-constexpr int NACC = 28;
+constexpr int NACC = 29;
+constexpr int ACC_B = 21, ACC_SUMR = 27, ACC_CNT = 28;
 constexpr int PARTIAL_STRIDE = 32;
 
 struct ChunkDesc {

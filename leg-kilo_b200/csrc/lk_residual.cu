@@ -228,7 +228,7 @@ __device__ __forceinline__ bool point_row(float4 pt, const ScanConst& sc, const 
 __device__ void scan_solve(const ResidualArgs& a, uint32_t scan, double* sm /* >= 512 doubles */) {
     const int tid = threadIdx.x;
     ScanStep st = a.step[scan];
-    double* sAcc = sm;        // 28
+    double* sAcc = sm;        // NACC
     double* sY = sm + 32;     // y[6] | W[36] row-major 6x6 | flag
     double* sDelta = sm + 80; // 30
     double* sProw = sm + 112; // 6 x 30 old rows of P
@@ -240,12 +240,12 @@ __device__ void scan_solve(const ResidualArgs& a, uint32_t scan, double* sm /* >
         sAcc[tid] = acc;
     }
     __syncthreads();
-    const double cnt = sAcc[27];
+    const double cnt = sAcc[ACC_CNT];
     if (cnt > 0.5) {
         if (tid == 0) {
             double A[36], rhs[42], M[36];
             double scale = 1.0;
-            if (cnt < 1.5) scale = sAcc[26] / (sAcc[26] + 0.0001);  // N == 1 adds 1e-4 to S (eskf.cc:100)
+            if (cnt < 1.5) scale = sAcc[ACC_SUMR] / (sAcc[ACC_SUMR] + 0.0001);  // N == 1 adds 1e-4 to S (eskf.cc:100)
             int q = 0;
             for (int i = 0; i < 6; ++i)
                 for (int j = i; j < 6; ++j) {
@@ -367,8 +367,8 @@ __global__ void __launch_bounds__(BLOCK) k_residual(const __grid_constant__ Resi
                 for (int c = r; c < 6; ++c) acc[q++] += hw * row.h[c];
                 acc[21 + r] += hw * row.z;
             }
-            acc[26] += row.R;
-            acc[27] += 1.0;
+            acc[ACC_SUMR] += row.R;
+            acc[ACC_CNT] += 1.0;
         }
     }
     if (DEBUG) return;
