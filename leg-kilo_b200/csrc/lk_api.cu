@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "lk_kernels.h"
+#include "lk_mapdev.h"
 
 using namespace lk;
 
@@ -53,11 +54,7 @@ struct lk_context {
     int gather_mode = 0;
 
     // map
-    DevBuf slots, nodes, aux, points, roots_tmp, flag;
-    uint64_t hash_cap = 0;
-    uint32_t n_roots = 0, n_nodes = 0;
-    uint64_t n_points = 0;
-    uint64_t reserve_roots = 0, reserve_nodes = 0, reserve_points = 0;
+    MapDevHost map;
 
     // staged batch
     int batch = 0;
@@ -122,18 +119,6 @@ void fill_globals(lk_context* c, const double* extR, const double* extT) {
     for (int i = 0; i < 5; ++i) g.layer_init_num[i] = c->mc.layer_init_num[i];
 }
 
-int ensure_hash(lk_context* c, uint64_t n_roots_wanted) {
-    uint64_t want = next_pow2(std::max<uint64_t>(1024, 2 * std::max(n_roots_wanted, c->reserve_roots)));
-    if (want > (1ull << 31)) return fail(c, LK_ERR_CAPACITY, "root table too large");
-    if (want != c->hash_cap) {
-        LK_CUDA(c, c->slots.ensure(want * sizeof(HashSlot)));
-        c->hash_cap = want;
-    }
-    launch_hash_clear(c->slots.as<HashSlot>(), c->hash_cap, c->stream);
-    LK_CUDA(c, cudaGetLastError());
-    return LK_OK;
-}
-
 uint32_t chunk_size_for(uint32_t n) {
     // a function of the bucket alone, so results are bitwise independent of how a batch is
     // sharded across GPUs (SURVEY §4 multi-GPU invariant)
@@ -157,9 +142,9 @@ ResidualArgs residual_args(lk_context* c) {
     ResidualArgs a;
     std::memset(&a, 0, sizeof(a));
     a.pts = c->pts.as<float4>();
-    a.slots = c->slots.as<HashSlot>();
-    a.hash_mask = (uint32_t)(c->hash_cap - 1);
-    a.nodes = c->nodes.as<MapNode>();
+    a.slots = c->map.slots;
+    a.hash_mask = (uint32_t)(c->map.hash_cap - 1);
+    a.nodes = c->map.nodes;
     a.chunks = c->chunks.as<ChunkDesc>();
     a.sc = c->sc.as<ScanConst>();
     a.step = c->step.as<ScanStep>();
@@ -218,7 +203,8 @@ int lk_destroy(lk_handle h) {
     if (!h) return LK_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->slots, &h->nodes, &h->aux, &h->points, &h->roots_tmp, &h->flag, &h->pts, &h->world,
+    h->map.release();
+    DevBuf* bufs[] = {&h->pts, &h->world,
                       &h->chunks, &h->stepinit, &h->x_in, &h->P_in, &h->clk_in, &h->Q, &h->x, &h->P, &h->clk, &h->sc,
                       &h->step, &h->partial, &h->ticket, &h->n_eff, &h->dbg_ok, &h->dbg_h, &h->dbg_z, &h->dbg_R,
                       &h->dbg_key, &h->tmp};
@@ -292,106 +278,58 @@ int lk_sync(lk_handle h) {
 
 int lk_map_reserve(lk_handle h, uint64_t max_roots, uint64_t max_nodes, uint64_t max_points) {
     if (!h) return LK_ERR_INVALID_ARG;
-    h->reserve_roots = max_roots;
-    h->reserve_nodes = max_nodes;
-    h->reserve_points = max_points;
+    h->map.reserve_roots = max_roots;
+    h->map.reserve_nodes = max_nodes;
+    h->map.reserve_points = max_points;
     return LK_OK;
 }
 
 int lk_map_upload(lk_handle h, const void* blob, size_t bytes) {
     if (!h || !blob) return fail(h, LK_ERR_INVALID_ARG, "null argument");
     cudaSetDevice(h->device);
-    if (bytes < sizeof(lk_map_blob_header)) return fail(h, LK_ERR_BAD_BLOB, "blob shorter than its header");
-    lk_map_blob_header hd;
-    std::memcpy(&hd, blob, sizeof(hd));
-    if (hd.magic != LK_MAP_MAGIC || hd.version != 1) return fail(h, LK_ERR_BAD_BLOB, "bad magic / version");
-    size_t need = sizeof(hd) + (size_t)hd.n_roots * sizeof(lk_map_root) + (size_t)hd.n_nodes * sizeof(lk_map_node) +
-                  (size_t)hd.n_nodes * sizeof(lk_map_aux) + (size_t)hd.n_points * sizeof(lk_map_point);
-    if (bytes < need) return fail(h, LK_ERR_BAD_BLOB, "blob truncated");
-    const char* p = (const char*)blob + sizeof(hd);
-    const lk_map_root* roots = (const lk_map_root*)p;
-    p += (size_t)hd.n_roots * sizeof(lk_map_root);
-    const lk_map_node* nodes = (const lk_map_node*)p;
-    p += (size_t)hd.n_nodes * sizeof(lk_map_node);
-    const lk_map_aux* aux = (const lk_map_aux*)p;
-    p += (size_t)hd.n_nodes * sizeof(lk_map_aux);
-    const lk_map_point* pts = (const lk_map_point*)p;
-    for (uint32_t r = 0; r < hd.n_roots; ++r)
-        if (roots[r].node < 0 || (uint32_t)roots[r].node >= hd.n_nodes) return fail(h, LK_ERR_BAD_BLOB, "root node index out of range");
-
-    int rc = ensure_hash(h, hd.n_roots);
-    if (rc) return rc;
-    size_t node_cap = std::max<uint64_t>(hd.n_nodes, h->reserve_nodes);
-    size_t point_cap = std::max<uint64_t>(hd.n_points, h->reserve_points);
-    LK_CUDA(h, h->nodes.ensure(std::max<size_t>(node_cap, 1) * sizeof(MapNode)));
-    LK_CUDA(h, h->aux.ensure(std::max<size_t>(node_cap, 1) * sizeof(MapAux)));
-    LK_CUDA(h, h->points.ensure(std::max<size_t>(point_cap, 1) * sizeof(MapPoint)));
-    LK_CUDA(h, h->roots_tmp.ensure(std::max<size_t>(hd.n_roots, 1) * sizeof(lk_map_root)));
-    LK_CUDA(h, h->flag.ensure(64));
-    LK_CUDA(h, cudaMemcpyAsync(h->nodes.p, nodes, (size_t)hd.n_nodes * sizeof(MapNode), cudaMemcpyHostToDevice, h->stream));
-    LK_CUDA(h, cudaMemcpyAsync(h->aux.p, aux, (size_t)hd.n_nodes * sizeof(MapAux), cudaMemcpyHostToDevice, h->stream));
-    LK_CUDA(h, cudaMemcpyAsync(h->points.p, pts, (size_t)hd.n_points * sizeof(MapPoint), cudaMemcpyHostToDevice, h->stream));
-    LK_CUDA(h, cudaMemcpyAsync(h->roots_tmp.p, roots, (size_t)hd.n_roots * sizeof(lk_map_root), cudaMemcpyHostToDevice, h->stream));
-    LK_CUDA(h, cudaMemsetAsync(h->flag.p, 0, 64, h->stream));
-    launch_hash_insert_roots(h->slots.as<HashSlot>(), (uint32_t)(h->hash_cap - 1), h->roots_tmp.as<lk_map_root>(),
-                             hd.n_roots, h->flag.as<uint32_t>(), h->stream);
-    LK_CUDA(h, cudaGetLastError());
-    uint32_t failed = 0;
-    LK_CUDA(h, cudaMemcpyAsync(&failed, h->flag.p, 4, cudaMemcpyDeviceToHost, h->stream));
-    LK_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (failed) return fail(h, LK_ERR_CAPACITY, "root table overflow");
-    h->n_roots = hd.n_roots;
-    h->n_nodes = hd.n_nodes;
-    h->n_points = hd.n_points;
-    return LK_OK;
+    std::string err;
+    int rc = map_upload_blob(h->map, h->g, blob, bytes, h->stream, err);
+    return rc ? fail(h, rc, err) : LK_OK;
 }
 
 int lk_map_stats(lk_handle h, uint64_t out[4]) {
     if (!h || !out) return LK_ERR_INVALID_ARG;
-    out[0] = h->n_roots;
-    out[1] = h->n_nodes;
-    out[2] = h->n_points;
-    out[3] = 0;
+    cudaSetDevice(h->device);
+    std::string err;
+    uint64_t planes = 0, live = 0;
+    int rc = map_count_planes(h->map, &planes, &live, h->stream, err);
+    if (rc) return fail(h, rc, err);
+    out[0] = h->map.n_roots;
+    out[1] = h->map.n_nodes;
+    out[2] = live;
+    out[3] = planes;
     return LK_OK;
 }
 
 int lk_map_download(lk_handle h, void* blob, size_t capacity, size_t* bytes_out) {
     if (!h) return LK_ERR_INVALID_ARG;
     cudaSetDevice(h->device);
-    size_t need = sizeof(lk_map_blob_header) + (size_t)h->n_roots * sizeof(lk_map_root) +
-                  (size_t)h->n_nodes * (sizeof(lk_map_node) + sizeof(lk_map_aux)) + (size_t)h->n_points * sizeof(lk_map_point);
-    if (bytes_out) *bytes_out = need;
-    if (!blob) return LK_OK;
-    if (capacity < need) return fail(h, LK_ERR_CAPACITY, "blob buffer too small");
-    lk_map_blob_header hd;
-    std::memset(&hd, 0, sizeof(hd));
-    hd.magic = LK_MAP_MAGIC;
-    hd.version = 1;
-    hd.n_roots = h->n_roots;
-    hd.n_nodes = h->n_nodes;
-    hd.n_points = h->n_points;
-    char* p = (char*)blob;
-    std::memcpy(p, &hd, sizeof(hd));
-    p += sizeof(hd);
-    LK_CUDA(h, h->roots_tmp.ensure(std::max<size_t>(h->n_roots, 1) * sizeof(lk_map_root)));
-    LK_CUDA(h, h->flag.ensure(64));
-    LK_CUDA(h, cudaMemsetAsync(h->flag.p, 0, 64, h->stream));
-    if (h->hash_cap) launch_hash_dump_roots(h->slots.as<HashSlot>(), h->hash_cap, h->roots_tmp.as<lk_map_root>(),
-                                            h->flag.as<uint32_t>(), h->stream);
-    LK_CUDA(h, cudaGetLastError());
-    LK_CUDA(h, cudaMemcpyAsync(p, h->roots_tmp.p, (size_t)h->n_roots * sizeof(lk_map_root), cudaMemcpyDeviceToHost, h->stream));
-    p += (size_t)h->n_roots * sizeof(lk_map_root);
-    LK_CUDA(h, cudaMemcpyAsync(p, h->nodes.p, (size_t)h->n_nodes * sizeof(MapNode), cudaMemcpyDeviceToHost, h->stream));
-    p += (size_t)h->n_nodes * sizeof(MapNode);
-    LK_CUDA(h, cudaMemcpyAsync(p, h->aux.p, (size_t)h->n_nodes * sizeof(MapAux), cudaMemcpyDeviceToHost, h->stream));
-    p += (size_t)h->n_nodes * sizeof(MapAux);
-    LK_CUDA(h, cudaMemcpyAsync(p, h->points.p, (size_t)h->n_points * sizeof(MapPoint), cudaMemcpyDeviceToHost, h->stream));
-    LK_CUDA(h, cudaStreamSynchronize(h->stream));
-    return LK_OK;
+    std::string err;
+    int rc = map_download_blob(h->map, blob, capacity, bytes_out, h->stream, err);
+    return rc ? fail(h, rc, err) : LK_OK;
 }
 
-int lk_map_build(lk_handle h, const float*, const float*, size_t, const double*, const double*, const double*) {
-    return fail(h, LK_ERR_NOT_READY, "lk_map_build: device-side BuildVoxelMap not available in this build");
+int lk_map_build(lk_handle h, const float* xyz_world, const float* xyz_body, size_t n, const double* rot,
+                 const double* rot_cov, const double* pos_cov) {
+    if (!h || !rot || !rot_cov || !pos_cov || (n && (!xyz_world || !xyz_body))) return fail(h, LK_ERR_INVALID_ARG, "null argument");
+    if (n >= (1ull << 31)) return fail(h, LK_ERR_CAPACITY, "too many points for one build");
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    LK_CUDA(h, h->pts.ensure(std::max<size_t>(n, 1) * 12));
+    LK_CUDA(h, h->world.ensure(std::max<size_t>(n, 1) * 12));
+    if (n) {
+        LK_CUDA(h, cudaMemcpyAsync(h->world.p, xyz_world, n * 12, cudaMemcpyHostToDevice, s));
+        LK_CUDA(h, cudaMemcpyAsync(h->pts.p, xyz_body, n * 12, cudaMemcpyHostToDevice, s));
+    }
+    h->batch = 0;  // the staging buffers were borrowed
+    std::string err;
+    int rc = map_build_device(h->map, h->g, h->world.as<float>(), h->pts.as<float>(), (uint32_t)n, rot, rot_cov, pos_cov, s, err);
+    return rc ? fail(h, rc, err) : LK_OK;
 }
 
 // ---- batch staging / run / fetch ----------------------------------------------------------------
@@ -485,7 +423,7 @@ int lk_batch_run(lk_handle h, int iters, int update_map) {
     if (h->batch <= 0) return fail(h, LK_ERR_NOT_READY, "lk_batch_run before lk_batch_stage");
     if (iters < 1) return fail(h, LK_ERR_INVALID_ARG, "iters must be >= 1");
     if (update_map) return fail(h, LK_ERR_NOT_READY, "update_map: device-side UpdateVoxelMap not available in this build");
-    if (!h->hash_cap) return fail(h, LK_ERR_NOT_READY, "no map: call lk_map_upload or lk_map_build first");
+    if (!h->map.ready()) return fail(h, LK_ERR_NOT_READY, "no map: call lk_map_upload or lk_map_build first");
     cudaSetDevice(h->device);
     cudaStream_t s = h->stream;
     const int batch = h->batch;
@@ -589,7 +527,7 @@ int lk_scan_update(lk_handle h, int batch, lk_state* x_inout, double* P_inout, c
 int lk_debug_residuals(lk_handle h, const lk_state* x, const double* P, const float* pts, uint32_t n, uint8_t* ok_out,
                        double* h_out, double* z_out, double* R_out, int32_t* key_out) {
     if (!h || !x || !P || (!pts && n)) return fail(h, LK_ERR_INVALID_ARG, "null argument");
-    if (!h->hash_cap) return fail(h, LK_ERR_NOT_READY, "no map");
+    if (!h->map.ready()) return fail(h, LK_ERR_NOT_READY, "no map");
     std::vector<double> Q(900, 0.0);
     lk_stream_clock clk = {0.0, 0.0};
     uint32_t so[2] = {0, n}, sb[2] = {0, 1}, bo[2] = {0, n};

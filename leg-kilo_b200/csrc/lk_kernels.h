@@ -71,11 +71,4 @@ struct ReprojectArgs {
 };
 void launch_reproject(const ReprojectArgs& a, uint32_t n_chunks, cudaStream_t s);
 
-// ---- map --------------------------------------------------------------------------------------
-void launch_hash_clear(HashSlot* slots, uint64_t capacity, cudaStream_t s);
-void launch_hash_insert_roots(HashSlot* slots, uint32_t mask, const lk_map_root* roots, uint32_t n_roots,
-                              uint32_t* fail_flag, cudaStream_t s);
-void launch_hash_dump_roots(const HashSlot* slots, uint64_t capacity, lk_map_root* roots, uint32_t* counter,
-                            cudaStream_t s);
-
 }  // namespace lk

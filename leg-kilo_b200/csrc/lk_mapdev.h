@@ -1,0 +1,47 @@
+// lk_mapdev.h — host-side owner of the device map buffers (root table, node / aux / point pools,
+// allocator counters) and the entry points of the map translation units.
+#pragma once
+#include <string>
+
+#include "lk_device.cuh"
+
+namespace lk {
+
+struct DevPoint;
+struct MapDev;
+
+class MapDevHost {
+   public:
+    ~MapDevHost() { release(); }
+    // (Re)create an EMPTY map sized for at least these counts plus the reserve; clears the table.
+    int allocate(uint64_t roots, uint64_t nodes, uint64_t points, cudaStream_t s, std::string& err);
+    // Make sure pools can take `extra_*` more items (grows by reallocation + copy). No-op if they fit.
+    int ensure_headroom(uint64_t extra_roots, uint64_t extra_nodes, uint64_t extra_points, cudaStream_t s,
+                        std::string& err);
+    void release();
+    MapDev dev() const;
+    bool ready() const { return hash_cap != 0; }
+    // pull the device allocator counters into the host mirrors
+    int sync_counters(cudaStream_t s, std::string& err);
+    int push_counters(cudaStream_t s, std::string& err);
+
+    HashSlot* slots = nullptr;
+    MapNode* nodes = nullptr;
+    MapAux* aux = nullptr;
+    DevPoint* points = nullptr;
+    uint32_t* counters = nullptr;  // [0] n_nodes [1] n_roots [2] overflow [4..5] n_points (u64)
+    uint64_t hash_cap = 0, node_cap = 0, point_cap = 0;
+    uint32_t n_roots = 0, n_nodes = 0;
+    uint64_t n_points = 0;  // bump pointer (slots handed out), not the number of live points
+    uint64_t reserve_roots = 0, reserve_nodes = 0, reserve_points = 0;
+};
+
+// lk_mapbuild.cu
+int map_build_device(MapDevHost& mh, const Globals& g, const float* d_xyz_world, const float* d_xyz_body, uint32_t n,
+                     const double* rot, const double* rot_cov, const double* pos_cov, cudaStream_t s, std::string& err);
+// lk_mapio.cu
+int map_upload_blob(MapDevHost& mh, const Globals& g, const void* blob, size_t bytes, cudaStream_t s, std::string& err);
+int map_download_blob(MapDevHost& mh, void* blob, size_t capacity, size_t* bytes_out, cudaStream_t s, std::string& err);
+int map_count_planes(MapDevHost& mh, uint64_t* planes, uint64_t* live_points, cudaStream_t s, std::string& err);
+
+}  // namespace lk
