@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — LiDAR points/sec through the ESKF point-to-plane update (BASELINE.json metric).
+
+Default workload = BASELINE.json configs[1]: leg_fusion, 16-line Velodyne ~28.8 k pts/scan,
+3 ESKF iterations, ~1 M-voxel map, batch = 1 per launch sequence, one B200. One STEP = one scan
+through the whole hot path (predict/prepare -> 3 x [residual + reduce + solve] -> re-projection).
+A ring of `--scans` distinct scans (default 512 = 236 MB of points, spread over 64 rooms of a
+500 m x 500 m map, > the 126 MB L2) is staged in HBM; step i processes scan i mod ring, so
+consecutive steps touch different points and different map regions ("inputs larger than L2").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+  torchrun --nproc-per-node N bench.py --gpus N ...    (one rank per GPU; scans shard, no collective)
+
+Prints ONE JSON line (rank 0). Point-iteration = one point through one iteration.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "leg-kilo_b200", "python"))
+
+from legkilo_b200 import abi, synth  # noqa: E402
+
+ALG_BYTES_PER_POINT_ITER = 304  # 16 point + 16 hash slot + 256 plane record + 16 world store
+
+WORKLOADS = {
+    # name: (config, lidar, iters, scans per launch (batch), default ring size, ground half extent, room grid)
+    "leg_fusion_b1": dict(cfg="leg_fusion", lidar="VLP16", iters=3, batch=1, ring=512, half=250.0, rooms=8,
+                          baseline_config="configs[1]: leg_fusion 16-line ~28.8k pts/scan, 3 iters, ~1M-voxel map, batch=1"),
+    "diter_b128": dict(cfg="diter", lidar="OS64", iters=3, batch=128, ring=128, half=250.0, rooms=8,
+                       baseline_config="configs[2]: Diter++ OS-64 ~131k pts/scan, 3 iters, batch=128"),
+    "small": dict(cfg="leg_fusion", lidar="VLP16", iters=3, batch=1, ring=16, half=40.0, rooms=1,
+                  baseline_config="smoke-size variant of configs[1]"),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def build_workload(w, rank, ring):
+    """Synthetic map cloud + a ring of scans. Returns dict of numpy arrays."""
+    cfg = abi.CONFIGS[w["cfg"]]
+    R, t = abi.extrinsics(cfg)
+    rooms = synth.BoxScene.room_grid(w["rooms"]) if w["rooms"] > 1 else None
+    scene = synth.BoxScene(ground_half_extent=w["half"], rooms=rooms)
+    pw, pb = scene.map_points(ext_R=R, ext_t=t)
+    lidar = getattr(synth, w["lidar"])
+    nrooms = len(scene.rooms)
+    rv, tv = synth.random_poses(ring, 2e-3 * 5, 0.02 * 5, stream=1000 + rank)  # "perturbation 5x larger" (SURVEY §8d cfg 2)
+    scans = [scene.scan(rotvec=rv[i], trans=tv[i], ext_R=R, ext_t=t, blind=cfg["blind"],
+                        stream=2000 + rank * 100000 + i, room=(i * 7 + rank) % nrooms, **lidar) for i in range(ring)]
+    offs = np.concatenate([[0], np.cumsum([len(s) for s in scans])]).astype(np.uint32)
+    # prior of every scan: default state placed at its room centre (the true pose is the prior
+    # perturbed by rv / tv)
+    x0 = abi.default_states(ring)
+    for i in range(ring):
+        cx, cy = scene.rooms[(i * 7 + rank) % nrooms]
+        x0["pos"][i] = (cx, cy, 0.0)
+    return dict(cfg=cfg, scene=scene, map_world=pw, map_body=pb, scans=scans, pts=np.concatenate(scans),
+                offs=offs, rv=rv, tv=tv, x0=x0)
+
+
+def cpu_reference_run(wl, w, scan_ids, nthreads, gain_information=True):
+    """The CPU restatement (oracle/) on a bounded sample: for each sampled scan the oracle builds the
+    map of that scan's room from the SAME synthetic cloud (BuildVoxelMap) and runs
+    KILO::predictUpdatePoint. Returns (seconds in the update loop, states, covs, n_eff)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lko
+    cfg = wl["cfg"]
+    scene = wl["scene"]
+    rooms = sorted({(i * 7 + wl["rank"]) % len(scene.rooms) for i in scan_ids})
+    pw, pb = wl["map_world"], wl["map_body"]
+    keep = np.zeros(len(pw), bool)
+    for r in rooms:
+        cx, cy = scene.rooms[r]
+        keep |= (np.abs(pw[:, 0] - cx) < scene.W + 2.25) & (np.abs(pw[:, 1] - cy) < scene.W + 2.25)
+    o = lko.Oracle(cfg)
+    o.build_voxel_map(pw[keep], pb[keep])
+    o.set_filter(None, None, abi.process_cov_Q(cfg), None)
+    n = len(scan_ids)
+    pts = np.concatenate([wl["scans"][i] for i in scan_ids])
+    offs = np.concatenate([[0], np.cumsum([len(wl["scans"][i]) for i in scan_ids])]).astype(np.uint32)
+    sec, xo, Po, ne = o.batch_run(wl["x0"][scan_ids], abi.init_cov(n), np.zeros(n, abi.CLOCK_DTYPE), pts, offs,
+                                  np.zeros(n), iters=w["iters"],
+                                  gain_mode=lko.GAIN_INFORMATION if gain_information else lko.GAIN_LITERAL,
+                                  nthreads=nthreads)
+    return sec, xo, Po, ne, int(offs[-1])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4096)
+    ap.add_argument("--warmup", type=int, default=512)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="leg_fusion_b1", choices=sorted(WORKLOADS))
+    ap.add_argument("--scans", type=int, default=0, help="ring size (distinct scans staged in HBM)")
+    ap.add_argument("--e2e-steps", type=int, default=256)
+    ap.add_argument("--cpu-scans", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather-mode", type=int, default=-1)
+    ap.add_argument("--fused", type=int, default=-1, help="0 = force the multi-kernel path for batch-of-one runs")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ring = args.scans or w["ring"]
+    ring = max(ring, w["batch"])
+    K, W = max(args.steps, 1), max(args.warmup, 3)
+    hbm_peak, peak_src = measured_peaks()
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        wl = build_workload(w, 0, max(args.cpu_scans, 4))
+        wl["rank"] = 0
+        ncores = os.cpu_count() or 1
+        per_step = max(ncores, 1)  # one scan per host thread per step
+        ids = list(range(min(per_step, len(wl["scans"]))))
+        for _ in range(max(1, min(W, 2))):
+            cpu_reference_run(wl, w, ids, ncores)
+        steps = max(1, min(K, 3))
+        tot_s, tot_pts = 0.0, 0
+        for _ in range(steps):
+            sec, _, _, _, npts = cpu_reference_run(wl, w, ids, ncores)
+            tot_s += sec
+            tot_pts += npts * w["iters"]
+        val = tot_pts / tot_s
+        line = dict(metric="LiDAR point-iterations/sec through the ESKF point-to-plane update", value=val,
+                    unit="point-iterations/s", impl="reference", n_gpus=args.gpus, steps=steps, warmup=min(W, 2),
+                    ms_per_step=1e3 * tot_s / steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f64", data="synthetic",
+                    config=dict(workload=args.workload, baseline_config=w["baseline_config"], iters=w["iters"],
+                                note="CPU restatement of the reference path (oracle/, information-form gain), one scan per host thread"),
+                    cpu_baseline=dict(value=val, unit="point-iterations/s", cores=ncores, kind="port",
+                                      sample=f"{len(ids)} scans x ~{len(wl['scans'][0])} pts x {w['iters']} iters per step, {steps} steps"),
+                    e2e=dict(value=val, unit="point-iterations/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (CUDA)
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from legkilo_b200 import Engine, pinned_empty
+
+    t_setup = time.time()
+    wl = build_workload(w, rank, ring)
+    wl["rank"] = rank
+    cfg = wl["cfg"]
+    eng = Engine(cfg, device=local_rank)
+    if args.gather_mode >= 0:
+        eng.set_param("gather_mode", args.gather_mode)
+    if args.fused >= 0:
+        eng.set_param("fused", args.fused)
+    eng.map_build(wl["map_world"], wl["map_body"])
+    mstats = eng.map_stats()
+    nsc = ring
+    Q = abi.process_cov_Q(cfg)
+    x0, P0, clk0 = wl["x0"], abi.init_cov(nsc), np.zeros(nsc, abi.CLOCK_DTYPE)
+    eng.stage(x0, P0, Q, clk0, wl["pts"], wl["offs"], np.zeros(nsc))
+    B = w["batch"]
+    groups = nsc // B  # step g processes scans [g*B, (g+1)*B)
+    pts_per_group = [int(wl["offs"][(g + 1) * B] - wl["offs"][g * B]) for g in range(groups)]
+    setup_s = time.time() - t_setup
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # warm-up (also warms the ring once when W >= groups)
+    for i in range(W):
+        eng.run_range((i % groups) * B, B, iters=w["iters"])
+    eng.sync()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    eng.timer_start()
+    work = 0
+    for i in range(K):
+        g = i % groups
+        eng.run_range(g * B, B, iters=w["iters"])
+        work += pts_per_group[g] * w["iters"]
+    tm = eng.timer_stop()
+    clocks = sampler.stop()
+    barrier()
+    elapsed_ms = tm["total_ms"]
+    if dist is not None:
+        import torch
+        tt = torch.tensor([elapsed_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tt.item())
+        ww = torch.tensor([float(work)], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(ww, op=dist.ReduceOp.SUM)
+        total_work = float(ww.item())
+    else:
+        total_work = float(work)
+    value = total_work / (elapsed_ms * 1e-3)
+
+    # roofline of the dominant kernel (k_residual): algorithmic bytes / its own event-timed duration
+    r_launches = max(tm["residual_launches"], 1)
+    res_ms = tm["residual_ms"] / r_launches
+    alg_bytes_per_launch = ALG_BYTES_PER_POINT_ITER * (work / r_launches)
+    achieved = alg_bytes_per_launch / (res_ms * 1e-3) / 1e9 if res_ms > 0 else 0.0
+    roofline = dict(bound="hbm", kernel="k_residual", achieved=achieved, peak=hbm_peak, unit="GB/s",
+                    frac=achieved / hbm_peak, traffic=None, peak_source=peak_src,
+                    alg_bytes_per_launch=alg_bytes_per_launch, avg_launch_us=res_ms * 1e3,
+                    share_of_step=tm["residual_ms"] / tm["total_ms"] if tm["total_ms"] > 0 else None)
+
+    # CPU baseline (rank 0, N=1 only) on a bounded sample + pose error of the GPU against it
+    cpu_baseline, pose = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ids = list(range(min(args.cpu_scans, nsc)))
+        sec, xo, Po, ne_cpu, npts = cpu_reference_run(wl, w, ids, 1)
+        cpu_val = npts * w["iters"] / sec
+        cpu_baseline = dict(value=cpu_val, unit="point-iterations/s", cores=1, kind="port",
+                            sample=f"{len(ids)} scans x ~{npts // len(ids)} pts x {w['iters']} iters, 1 thread (reference loop is serial), information-form gain",
+                            host_cores_available=os.cpu_count())
+        # same scans on the GPU (full map), compare state / covariance
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import lko
+        eng.run_range(0, len(ids), iters=w["iters"])
+        eng.sync()
+        out = eng.fetch(want_world=False)
+        ex, eP = 0.0, 0.0
+        for j, i in enumerate(ids):
+            num = np.abs(lko.boxminus(out["x"][i:i + 1], xo[j:j + 1])).max()
+            den = max(np.abs(lko.boxminus(xo[j:j + 1], x0[i:i + 1])).max(), 1e-12)
+            ex = max(ex, num / den)
+            eP = max(eP, np.abs(out["P"][i] - Po[j]).max() / np.abs(Po[j]).max())
+        pose = dict(pose_rel_err_max=ex, cov_rel_err_max=eP, scans_checked=len(ids),
+                    n_eff_equal=bool(np.array_equal(out["n_eff"][ids], ne_cpu)))
+
+    # end-to-end through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region)
+    e2e = None
+    if (rank == 0 or world > 1) and not args.no_e2e:
+        E = max(8, min(args.e2e_steps, K))
+        maxp = max(pts_per_group)
+        h_pts = pinned_empty((maxp, 4), np.float32)
+        h_world = pinned_empty((maxp, 4), np.float32)
+        Ps = abi.init_cov(B); cs = np.zeros(B, abi.CLOCK_DTYPE)
+        t_e2e, work_e2e, h2d, d2h = 0.0, 0, 0, 0
+        from legkilo_b200 import _p, lib
+        for i in range(E + 3):
+            g = i % groups
+            o0, o1 = int(wl["offs"][g * B]), int(wl["offs"][(g + 1) * B])
+            n = o1 - o0
+            h_pts[:n] = wl["pts"][o0:o1]  # producer side (outside the timed region)
+            so = (wl["offs"][g * B:(g + 1) * B + 1] - wl["offs"][g * B]).astype(np.uint32)
+            sbp = np.arange(B + 1, dtype=np.uint32)
+            bt = np.zeros(B)
+            xi, Pi, ci = x0[g * B:(g + 1) * B].copy(), Ps.copy(), cs.copy()
+            ne = np.zeros(B, np.uint32)
+            t0 = time.perf_counter()
+            rc = lib().lk_scan_update(eng.h, B, _p(xi), _p(Pi), _p(Q), _p(ci), _p(h_pts), _p(so), _p(sbp), _p(so),
+                                      _p(bt), w["iters"], 0, _p(h_world), _p(ne))
+            t1 = time.perf_counter()
+            assert rc == 0, lib().lk_last_error(eng.h)
+            if i >= 3:
+                t_e2e += t1 - t0
+                work_e2e += n * w["iters"]
+                h2d = n * 16 + B * (288 + 7200 + 16) + 7200
+                d2h = n * 16 + B * (288 + 7200 + 16 + 4)
+        e2e_val = work_e2e / t_e2e
+        if dist is not None:
+            import torch
+            tv = torch.tensor([e2e_val], dtype=torch.float64, device=f"cuda:{local_rank}")
+            dist.all_reduce(tv, op=dist.ReduceOp.SUM)
+            e2e_val = float(tv.item())
+        e2e = dict(value=e2e_val, unit="point-iterations/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                   steps=E, note="lk_scan_update per step, pinned host buffers, wall clock incl. staging + sync")
+
+    if rank == 0:
+        line = dict(metric="LiDAR point-iterations/sec through the ESKF point-to-plane update", value=value,
+                    unit="point-iterations/s", n_gpus=world, steps=K, warmup=W, ms_per_step=elapsed_ms / K,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                    config=dict(workload=args.workload, baseline_config=w["baseline_config"], iters=w["iters"],
+                                scans_per_step=B, points_per_scan=int(np.mean([len(s) for s in wl["scans"]])),
+                                ring_scans=nsc, ring_bytes=int(wl["pts"].nbytes), map=mstats,
+                                l2_policy="inputs larger than L2: ring of distinct scans over distinct map regions",
+                                parallelism=f"scans sharded over {world} GPU(s), no collective"),
+                    gpu_launches=int(tm["launches"]), roofline=roofline, cpu_baseline=cpu_baseline, e2e=e2e,
+                    pose_vs_cpu=pose, clocks=clocks, setup_s=setup_s)
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

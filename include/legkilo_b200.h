@@ -246,6 +246,15 @@ int lk_batch_stage(lk_handle h, int batch, const lk_state* x, const double* P, c
 int lk_batch_run(lk_handle h, int iters, int update_map);
 int lk_batch_fetch(lk_handle h, lk_state* x_out, double* P_out, lk_stream_clock* clk_out,
                    float* pts_world_out, uint32_t* n_effective_out);
+/* Asynchronous form: enqueue the hot path for scans [first, first+count) of the staged batch on
+ * the library's stream and return without synchronising (pipelined steps). */
+int lk_batch_run_range(lk_handle h, uint32_t first, uint32_t count, int iters, int update_map);
+/* CUDA-event timer on the library's stream: start records an event, stop records another,
+ * synchronises and reports the elapsed device time, the time inside the residual kernel (when
+ * "kernel_timing" is on), and the number of kernels launched in between. */
+int lk_timer_start(lk_handle h);
+int lk_timer_stop(lk_handle h, float* total_ms, float* residual_kernel_ms, uint32_t* n_kernel_launches,
+                  uint32_t* n_residual_launches);
 /* Device time of the most recent lk_batch_run (CUDA events on the library's stream), and the
  * number of kernels it launched / time spent in the residual kernel alone. */
 int lk_batch_last_timing(lk_handle h, float* total_ms, float* residual_kernel_ms,

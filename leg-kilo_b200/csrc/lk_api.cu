@@ -59,16 +59,24 @@ struct lk_context {
     // staged batch
     int batch = 0;
     uint64_t total_pts = 0;
-    uint32_t total_chunks = 0, n_steps = 0;
+    uint32_t total_chunks = 0, n_steps = 0, max_chunk_pts = 0;
     std::vector<uint32_t> step_chunk_ptr;
     DevBuf pts, world, chunks, stepinit, x_in, P_in, clk_in, Q, x, P, clk, sc, step, partial, ticket, n_eff;
-    DevBuf dbg_ok, dbg_h, dbg_z, dbg_R, dbg_key, tmp;
+    DevBuf dbg_ok, dbg_h, dbg_z, dbg_R, dbg_key, tmp, trace, bar;
+    int trace_on = 0;
+    int use_fused = 1;      // batch-of-one runs go through the persistent per-scan kernel
+    int fused_parity = 0;
+    uint32_t fused_launches = 0;
 
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> kev;
     float last_total_ms = 0, last_residual_ms = 0;
     uint32_t last_launches = 0, last_residual_launches = 0;
+    uint32_t acc_launches = 0, acc_residual_launches = 0;
+    size_t nev = 0;
+    int kernel_timing = 1;
+    std::vector<StepInit> h_inits;
 };
 
 namespace {
@@ -121,8 +129,9 @@ void fill_globals(lk_context* c, const double* extR, const double* extT) {
 
 uint32_t chunk_size_for(uint32_t n) {
     // a function of the bucket alone, so results are bitwise independent of how a batch is
-    // sharded across GPUs (SURVEY §4 multi-GPU invariant)
-    uint32_t c = (n + 63) / 64;
+    // sharded across GPUs (SURVEY §4 multi-GPU invariant). Small buckets: one point per thread
+    // (256-point chunks) for latency; large buckets: at most 512 chunks per bucket.
+    uint32_t c = (n + 511) / 512;
     c = ((c + 255) / 256) * 256;
     if (c < 256) c = 256;
     if (c > 4096) c = 4096;
@@ -154,6 +163,7 @@ ResidualArgs residual_args(lk_context* c) {
     a.P = c->P.as<double>();
     a.clk = c->clk.as<lk_stream_clock>();
     a.n_eff = c->n_eff.as<uint32_t>();
+    a.trace = c->trace_on ? c->trace.as<unsigned long long>() : nullptr;
     a.g = c->g;
     return a;
 }
@@ -207,7 +217,7 @@ int lk_destroy(lk_handle h) {
     DevBuf* bufs[] = {&h->pts, &h->world,
                       &h->chunks, &h->stepinit, &h->x_in, &h->P_in, &h->clk_in, &h->Q, &h->x, &h->P, &h->clk, &h->sc,
                       &h->step, &h->partial, &h->ticket, &h->n_eff, &h->dbg_ok, &h->dbg_h, &h->dbg_z, &h->dbg_R,
-                      &h->dbg_key, &h->tmp};
+                      &h->dbg_key, &h->tmp, &h->trace, &h->bar};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : h->kev) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -254,6 +264,17 @@ int lk_host_free(void* p) {
 int lk_set_param(lk_handle h, const char* name, double value) {
     if (!h || !name) return LK_ERR_INVALID_ARG;
     if (!std::strcmp(name, "gather_mode")) { h->gather_mode = (int)value; return LK_OK; }
+    if (!std::strcmp(name, "kernel_timing")) { h->kernel_timing = (int)value; return LK_OK; }
+    if (!std::strcmp(name, "fused")) { h->use_fused = (int)value; return LK_OK; }
+    if (!std::strcmp(name, "trace")) {
+        h->trace_on = (int)value;
+        if (h->trace_on) {
+            cudaSetDevice(h->device);
+            LK_CUDA(h, h->trace.ensure((size_t)(1 << 16) * 8 * 8));
+            LK_CUDA(h, cudaMemset(h->trace.p, 0, (size_t)(1 << 16) * 8 * 8));
+        }
+        return LK_OK;
+    }
     return fail(h, LK_ERR_INVALID_ARG, std::string("unknown parameter ") + name);
 }
 
@@ -261,7 +282,7 @@ int lk_set_param(lk_handle h, const char* name, double value) {
 int lk_debug_read(lk_handle h, int what, void* dst, size_t bytes) {
     if (!h || !dst) return LK_ERR_INVALID_ARG;
     cudaSetDevice(h->device);
-    DevBuf* b = what == 0 ? &h->partial : &h->sc;
+    DevBuf* b = what == 0 ? &h->partial : (what == 1 ? &h->sc : &h->trace);
     if (bytes > b->cap) bytes = b->cap;
     LK_CUDA(h, cudaMemcpy(dst, b->p, bytes, cudaMemcpyDeviceToHost));
     return LK_OK;
@@ -356,13 +377,15 @@ int lk_batch_stage(lk_handle h, int batch, const lk_state* x, const double* P, c
         }
     }
     std::vector<ChunkDesc> chunks;
-    std::vector<StepInit> inits((size_t)max_buckets * batch);
+    std::vector<StepInit>& inits = h->h_inits;
+    inits.assign((size_t)max_buckets * batch, StepInit());
     h->step_chunk_ptr.assign(max_buckets + 1, 0);
     for (uint32_t k = 0; k < max_buckets; ++k) {
         h->step_chunk_ptr[k] = (uint32_t)chunks.size();
         for (int s = 0; s < batch; ++s) {
             StepInit& in = inits[(size_t)k * batch + s];
             std::memset(&in, 0, sizeof(in));
+            in.chunk_begin = in.chunk_end = (uint32_t)chunks.size();
             uint32_t nb = scan_bucket_ptr[s + 1] - scan_bucket_ptr[s];
             if (k >= nb) continue;
             uint32_t b = scan_bucket_ptr[s] + k;
@@ -388,6 +411,8 @@ int lk_batch_stage(lk_handle h, int batch, const lk_state* x, const double* P, c
     h->batch = batch;
     h->total_pts = total;
     h->total_chunks = (uint32_t)chunks.size();
+    h->max_chunk_pts = 0;
+    for (const ChunkDesc& cd : chunks) h->max_chunk_pts = std::max(h->max_chunk_pts, cd.count);
     h->n_steps = max_buckets;
 
     LK_CUDA(h, h->pts.ensure(std::max<size_t>(total, 1) * 16));
@@ -403,7 +428,11 @@ int lk_batch_stage(lk_handle h, int batch, const lk_state* x, const double* P, c
     LK_CUDA(h, h->clk.ensure((size_t)batch * sizeof(lk_stream_clock)));
     LK_CUDA(h, h->sc.ensure((size_t)batch * sizeof(ScanConst)));
     LK_CUDA(h, h->step.ensure((size_t)batch * sizeof(ScanStep)));
-    LK_CUDA(h, h->partial.ensure(std::max<size_t>(chunks.size(), 1) * PARTIAL_STRIDE * 8));
+    LK_CUDA(h, h->partial.ensure(2 * std::max<size_t>(chunks.size(), 1) * PARTIAL_STRIDE * 8));
+    if (!h->bar.p) {
+        LK_CUDA(h, h->bar.ensure(64));
+        LK_CUDA(h, cudaMemsetAsync(h->bar.p, 0, 64, h->stream));
+    }
     LK_CUDA(h, h->ticket.ensure((size_t)batch * 4));
     LK_CUDA(h, h->n_eff.ensure((size_t)batch * 4));
     cudaStream_t s = h->stream;
@@ -418,23 +447,97 @@ int lk_batch_stage(lk_handle h, int batch, const lk_state* x, const double* P, c
     return LK_OK;
 }
 
-int lk_batch_run(lk_handle h, int iters, int update_map) {
+int lk_timer_start(lk_handle h) {
+    if (!h) return LK_ERR_INVALID_ARG;
+    cudaSetDevice(h->device);
+    h->nev = 0;
+    h->acc_launches = 0;
+    h->acc_residual_launches = 0;
+    LK_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    return LK_OK;
+}
+
+int lk_timer_stop(lk_handle h, float* total_ms, float* residual_kernel_ms, uint32_t* n_kernel_launches,
+                  uint32_t* n_residual_launches) {
+    if (!h) return LK_ERR_INVALID_ARG;
+    cudaSetDevice(h->device);
+    LK_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    LK_CUDA(h, cudaStreamSynchronize(h->stream));
+    LK_CUDA(h, cudaGetLastError());
+    LK_CUDA(h, cudaEventElapsedTime(&h->last_total_ms, h->ev0, h->ev1));
+    float rms = 0;
+    for (size_t i = 0; i + 1 < h->nev; i += 2) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->kev[i], h->kev[i + 1]);
+        rms += ms;
+    }
+    h->last_residual_ms = rms;
+    h->last_launches = h->acc_launches;
+    h->last_residual_launches = h->acc_residual_launches;
+    if (total_ms) *total_ms = h->last_total_ms;
+    if (residual_kernel_ms) *residual_kernel_ms = rms;
+    if (n_kernel_launches) *n_kernel_launches = h->last_launches;
+    if (n_residual_launches) *n_residual_launches = h->last_residual_launches;
+    return LK_OK;
+}
+
+// Enqueue the hot path for scans [first, first+count) of the staged batch; no host sync.
+int lk_batch_run_range(lk_handle h, uint32_t first, uint32_t count, int iters, int update_map) {
     if (!h) return LK_ERR_INVALID_ARG;
     if (h->batch <= 0) return fail(h, LK_ERR_NOT_READY, "lk_batch_run before lk_batch_stage");
     if (iters < 1) return fail(h, LK_ERR_INVALID_ARG, "iters must be >= 1");
+    if (count == 0 || first + count > (uint32_t)h->batch) return fail(h, LK_ERR_INVALID_ARG, "scan range outside the staged batch");
     if (update_map) return fail(h, LK_ERR_NOT_READY, "update_map: device-side UpdateVoxelMap not available in this build");
     if (!h->map.ready()) return fail(h, LK_ERR_NOT_READY, "no map: call lk_map_upload or lk_map_build first");
     cudaSetDevice(h->device);
     cudaStream_t s = h->stream;
     const int batch = h->batch;
-    LK_CUDA(h, cudaEventRecord(h->ev0, s));
-    LK_CUDA(h, cudaMemcpyAsync(h->x.p, h->x_in.p, (size_t)batch * sizeof(lk_state), cudaMemcpyDeviceToDevice, s));
-    LK_CUDA(h, cudaMemcpyAsync(h->P.p, h->P_in.p, (size_t)batch * 900 * 8, cudaMemcpyDeviceToDevice, s));
-    LK_CUDA(h, cudaMemcpyAsync(h->clk.p, h->clk_in.p, (size_t)batch * sizeof(lk_stream_clock), cudaMemcpyDeviceToDevice, s));
-    LK_CUDA(h, cudaMemsetAsync(h->n_eff.p, 0, (size_t)batch * 4, s));
-    uint32_t launches = 0, rlaunches = 0;
-    size_t nev = 0;
+    if (count == 1 && h->use_fused && h->max_chunk_pts <= 256) {
+        // one scan: the whole bucket loop in ONE persistent cooperative kernel (lk_fused.cu)
+        uint32_t max_chunks = 1;
+        for (uint32_t k = 0; k < h->n_steps; ++k) {
+            const StepInit& in = h->h_inits[(size_t)k * batch + first];
+            max_chunks = std::max(max_chunks, in.chunk_end - in.chunk_begin);
+        }
+        uint32_t grid = std::min<uint32_t>(max_chunks, (uint32_t)std::max(1, fused_max_blocks(h->device)));
+        FusedArgs fa;
+        std::memset(&fa, 0, sizeof(fa));
+        fa.pts = h->pts.as<float4>();
+        fa.world = h->world.as<float4>();
+        fa.chunks = h->chunks.as<ChunkDesc>();
+        fa.inits = h->stepinit.as<StepInit>();
+        fa.batch = batch;
+        fa.n_steps = h->n_steps;
+        fa.scan = first;
+        fa.partial = h->partial.as<double>();
+        fa.partial_stride = (size_t)std::max<uint32_t>(h->total_chunks, 1) * PARTIAL_STRIDE;
+        fa.x_in = h->x_in.as<double>();
+        fa.P_in = h->P_in.as<double>();
+        fa.clk_in = h->clk_in.as<lk_stream_clock>();
+        fa.Q = h->Q.as<double>();
+        fa.x = h->x.as<double>();
+        fa.P = h->P.as<double>();
+        fa.clk = h->clk.as<lk_stream_clock>();
+        fa.n_eff = h->n_eff.as<uint32_t>();
+        fa.bar = h->bar.as<uint32_t>();
+        fa.parity = h->fused_parity;
+        h->fused_parity ^= 1;
+        fa.iters = iters;
+        fa.mv.slots = h->map.slots;
+        fa.mv.hash_mask = (uint32_t)(h->map.hash_cap - 1);
+        fa.mv.nodes = h->map.nodes;
+        fa.trace = h->trace_on ? h->trace.as<unsigned long long>() : nullptr;
+        fa.g = h->g;
+        if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
+        LK_CUDA(h, launch_scan_fused(fa, grid, s));
+        if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
+        ++h->acc_launches;
+        ++h->acc_residual_launches;
+        return LK_OK;
+    }
     for (uint32_t k = 0; k < h->n_steps; ++k) {
+        const StepInit* hin = h->h_inits.data() + (size_t)k * batch;
+        uint32_t c0 = hin[first].chunk_begin, c1 = hin[first + count - 1].chunk_end;
         PredictArgs pa;
         pa.init = h->stepinit.as<StepInit>() + (size_t)k * batch;
         pa.step = h->step.as<ScanStep>();
@@ -444,19 +547,23 @@ int lk_batch_run(lk_handle h, int iters, int update_map) {
         pa.Q = h->Q.as<double>();
         pa.clk = h->clk.as<lk_stream_clock>();
         pa.ticket = h->ticket.as<uint32_t>();
-        pa.batch = batch;
+        pa.n_eff = h->n_eff.as<uint32_t>();
+        pa.x_in = h->x_in.as<double>();
+        pa.P_in = h->P_in.as<double>();
+        pa.clk_in = h->clk_in.as<lk_stream_clock>();
+        pa.reset = (k == 0) ? 1 : 0;
+        pa.scan_first = (int)first;
+        pa.batch = (int)count;
         launch_predict_prepare(pa, s);
-        ++launches;
-        uint32_t c0 = h->step_chunk_ptr[k], c1 = h->step_chunk_ptr[k + 1];
+        ++h->acc_launches;
         for (int it = 0; it < iters; ++it) {
             ResidualArgs ra = residual_args(h);
             ra.chunk_first = c0;
             ra.last_iter = (it == iters - 1) ? 1 : 0;
-            cudaEvent_t e0 = kev_get(h, nev++), e1 = kev_get(h, nev++);
-            cudaEventRecord(e0, s);
-            launch_residual(ra, c1 - c0, false, h->gather_mode, s);
-            cudaEventRecord(e1, s);
-            if (c1 > c0) { ++launches; ++rlaunches; }
+            if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
+            launch_residual(ra, c1 - c0, false, h->max_chunk_pts <= 256, s);
+            if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
+            if (c1 > c0) { ++h->acc_launches; ++h->acc_residual_launches; }
         }
         ReprojectArgs rp;
         rp.pts = h->pts.as<float4>();
@@ -467,22 +574,20 @@ int lk_batch_run(lk_handle h, int iters, int update_map) {
         rp.step = h->step.as<ScanStep>();
         rp.g = h->g;
         launch_reproject(rp, c1 - c0, s);
-        if (c1 > c0) ++launches;
+        if (c1 > c0) ++h->acc_launches;
     }
     LK_CUDA(h, cudaGetLastError());
-    LK_CUDA(h, cudaEventRecord(h->ev1, s));
-    LK_CUDA(h, cudaStreamSynchronize(s));
-    LK_CUDA(h, cudaEventElapsedTime(&h->last_total_ms, h->ev0, h->ev1));
-    float rms = 0;
-    for (size_t i = 0; i + 1 < nev; i += 2) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, h->kev[i], h->kev[i + 1]);
-        rms += ms;
-    }
-    h->last_residual_ms = rms;
-    h->last_launches = launches;
-    h->last_residual_launches = rlaunches;
     return LK_OK;
+}
+
+int lk_batch_run(lk_handle h, int iters, int update_map) {
+    if (!h) return LK_ERR_INVALID_ARG;
+    if (h->batch <= 0) return fail(h, LK_ERR_NOT_READY, "lk_batch_run before lk_batch_stage");
+    int rc = lk_timer_start(h);
+    if (rc) return rc;
+    rc = lk_batch_run_range(h, 0, (uint32_t)h->batch, iters, update_map);
+    if (rc) return rc;
+    return lk_timer_stop(h, nullptr, nullptr, nullptr, nullptr);
 }
 
 int lk_batch_fetch(lk_handle h, lk_state* x_out, double* P_out, lk_stream_clock* clk_out, float* pts_world_out,
@@ -542,9 +647,6 @@ int lk_debug_residuals(lk_handle h, const lk_state* x, const double* P, const fl
     LK_CUDA(h, h->dbg_z.ensure(nn * 8));
     LK_CUDA(h, h->dbg_R.ensure(nn * 8));
     LK_CUDA(h, h->dbg_key.ensure(nn * 12));
-    LK_CUDA(h, cudaMemcpyAsync(h->x.p, h->x_in.p, sizeof(lk_state), cudaMemcpyDeviceToDevice, s));
-    LK_CUDA(h, cudaMemcpyAsync(h->P.p, h->P_in.p, 900 * 8, cudaMemcpyDeviceToDevice, s));
-    LK_CUDA(h, cudaMemcpyAsync(h->clk.p, h->clk_in.p, sizeof(lk_stream_clock), cudaMemcpyDeviceToDevice, s));
     PredictArgs pa;
     pa.init = h->stepinit.as<StepInit>();
     pa.step = h->step.as<ScanStep>();
@@ -554,6 +656,12 @@ int lk_debug_residuals(lk_handle h, const lk_state* x, const double* P, const fl
     pa.Q = h->Q.as<double>();
     pa.clk = h->clk.as<lk_stream_clock>();
     pa.ticket = h->ticket.as<uint32_t>();
+    pa.n_eff = h->n_eff.as<uint32_t>();
+    pa.x_in = h->x_in.as<double>();
+    pa.P_in = h->P_in.as<double>();
+    pa.clk_in = h->clk_in.as<lk_stream_clock>();
+    pa.reset = 1;
+    pa.scan_first = 0;
     pa.batch = 1;
     launch_predict_prepare(pa, s);
     ResidualArgs ra = residual_args(h);
@@ -563,7 +671,7 @@ int lk_debug_residuals(lk_handle h, const lk_state* x, const double* P, const fl
     ra.dbg_z = h->dbg_z.as<double>();
     ra.dbg_R = h->dbg_R.as<double>();
     ra.dbg_key = h->dbg_key.as<int32_t>();
-    launch_residual(ra, h->total_chunks, true, 0, s);
+    launch_residual(ra, h->total_chunks, true, false, s);
     LK_CUDA(h, cudaGetLastError());
     if (n) {
         if (ok_out) LK_CUDA(h, cudaMemcpyAsync(ok_out, h->dbg_ok.p, n, cudaMemcpyDeviceToHost, s));

@@ -30,6 +30,12 @@ typedef lk_map_node MapNode;   // 256 B, first 232 B are what the residual kerne
 typedef lk_map_aux MapAux;     // 64 B
 typedef lk_map_point MapPoint; // 72 B
 
+struct MapView {  // what the residual path reads of the map
+    const HashSlot* slots;
+    uint32_t hash_mask;
+    const MapNode* nodes;
+};
+
 // ---- per-call constants (kernel parameter space) ------------------------------------------
 struct Globals {
     double Re[9];      // extrinsic rotation  (KILO::ext_rot_)
@@ -93,7 +99,9 @@ __device__ __forceinline__ void so3_exp3(double v1, double v2, double v3, double
     E[0] = 1; E[1] = 0; E[2] = 0; E[3] = 0; E[4] = 1; E[5] = 0; E[6] = 0; E[7] = 0; E[8] = 1;
     if (norm > 0.00001) {
         double kx = v1 / norm, ky = v2 / norm, kz = v3 / norm;
-        double s = sin(norm), c1 = 1.0 - cos(norm);
+        double s, c;
+        sincos(norm, &s, &c);
+        double c1 = 1.0 - c;
         double K[9] = {0, -kz, ky, kz, 0, -kx, -ky, kx, 0};
         double K2[9];
         mat3_mul(K, K, K2);
@@ -108,7 +116,9 @@ __device__ __forceinline__ void so3_exp_vec(double v1, double v2, double v3, dou
     E[0] = 1; E[1] = 0; E[2] = 0; E[3] = 0; E[4] = 1; E[5] = 0; E[6] = 0; E[7] = 0; E[8] = 1;
     if (norm > 0.0000001) {
         double kx = v1 / norm, ky = v2 / norm, kz = v3 / norm;
-        double s = sin(norm), c1 = 1.0 - cos(norm);
+        double s, c;
+        sincos(norm, &s, &c);
+        double c1 = 1.0 - c;
         double K[9] = {0, -kz, ky, kz, 0, -kx, -ky, kx, 0};
         double K2[9];
         mat3_mul(K, K, K2);

@@ -38,10 +38,12 @@ struct ResidualArgs {
     double* dbg_z;
     double* dbg_R;
     int32_t* dbg_key;
+    unsigned long long* trace;  // optional %globaltimer stamps: 8 per block + 8 for the tail
     Globals g;
 };
 
-void launch_residual(const ResidualArgs& a, uint32_t n_chunks, bool debug, int gather_mode, cudaStream_t s);
+// single: every chunk of the launch holds at most 128 points (one point per thread)
+void launch_residual(const ResidualArgs& a, uint32_t n_chunks, bool debug, bool single, cudaStream_t s);
 
 struct PredictArgs {
     const StepInit* init;  // [batch] for this step
@@ -52,7 +54,13 @@ struct PredictArgs {
     const double* Q;       // [900]
     lk_stream_clock* clk;  // [batch]
     uint32_t* ticket;
-    int batch;
+    uint32_t* n_eff;
+    const double* x_in;   // staged inputs, read when reset != 0
+    const double* P_in;
+    const lk_stream_clock* clk_in;
+    int reset;            // re-load the filter from the staged inputs first (only on a scan's first step)
+    int scan_first;  // first scan of the range this launch covers
+    int batch;       // scans in the range (grid.x)
 };
 void launch_predict_prepare(const PredictArgs& a, cudaStream_t s);
 
@@ -70,5 +78,36 @@ struct ReprojectArgs {
     Globals g;
 };
 void launch_reproject(const ReprojectArgs& a, uint32_t n_chunks, cudaStream_t s);
+
+
+// ---- fused per-scan persistent kernel (lk_fused.cu) -------------------------------------------
+struct FusedArgs {
+    const float4* pts;
+    float4* world;
+    const ChunkDesc* chunks;
+    const StepInit* inits;  // [n_steps][batch]
+    int batch;
+    uint32_t n_steps;
+    uint32_t scan;
+    double* partial;         // 2 x partial_stride doubles (double-buffered by iteration parity)
+    size_t partial_stride;
+    const double* x_in;
+    const double* P_in;
+    const lk_stream_clock* clk_in;
+    const double* Q;
+    double* x;
+    double* P;
+    lk_stream_clock* clk;
+    uint32_t* n_eff;
+    uint32_t* bar;  // [2] grid-barrier counters, used alternately by consecutive launches
+    int parity;
+    int iters;
+    MapView mv;
+    unsigned long long* trace;  // optional: 32 %globaltimer stamps per block
+    Globals g;
+};
+size_t fused_smem_bytes();
+int fused_max_blocks(int device);
+cudaError_t launch_scan_fused(const FusedArgs& a, uint32_t grid, cudaStream_t s);
 
 }  // namespace lk

@@ -91,7 +91,7 @@ MapDev MapDevHost::dev() const {
 }
 
 int MapDevHost::allocate(uint64_t roots, uint64_t nnodes, uint64_t npoints, cudaStream_t s, std::string& err) {
-    uint64_t want_hash = next_pow2(std::max<uint64_t>(1024, 2 * (roots + reserve_roots)));
+    uint64_t want_hash = next_pow2(std::max<uint64_t>(1024, 4 * (roots + reserve_roots)));  // load factor <= 0.25
     if (want_hash > (1ull << 31)) { err = "root table too large"; return LK_ERR_CAPACITY; }
     uint64_t want_nodes = std::max<uint64_t>(nnodes + reserve_nodes, 64);
     uint64_t want_points = std::max<uint64_t>(npoints + reserve_points, 64);
@@ -153,9 +153,9 @@ int MapDevHost::ensure_headroom(uint64_t extra_roots, uint64_t extra_nodes, uint
         cudaFree(points);
         points = np; point_cap = want;
     }
-    if (2 * (n_roots + extra_roots) > hash_cap) {
+    if (4 * (n_roots + extra_roots) > hash_cap) {
         // rehash: dump roots, rebuild a bigger table
-        uint64_t want = next_pow2(2 * (n_roots + extra_roots) + 2 * reserve_roots);
+        uint64_t want = next_pow2(4 * (n_roots + extra_roots) + 4 * reserve_roots);
         if (want > (1ull << 31)) { err = "root table too large"; return LK_ERR_CAPACITY; }
         lk_map_root* tmp = nullptr;
         MI_CUDA(cudaMalloc((void**)&tmp, std::max<size_t>(n_roots, 1) * sizeof(lk_map_root)));

@@ -1,0 +1,308 @@
+// lk_pass.cuh — one block-wide pass over up to NTHREADS points (one point per thread):
+//   1. transform, voxel key, home probe AND the speculative probe of the one neighbour voxel the
+//      reference falls back to (KILO.cc:156-178) — both 16-byte table reads are in flight together;
+//   2. every lane stages its 256-byte plane record into shared memory with one TMA bulk copy
+//      (cp.async.bulk global -> shared, completion on the warp's mbarrier) instead of 15 scattered
+//      128-bit loads per lane (32 cache lines per warp-instruction);
+//   3. gates + residual row from the staged record (conflict-free 128-bit shared loads, 272-byte
+//      slot stride);
+//   4. points whose home voxel gave no residual are compacted into a block-wide list and their
+//      neighbour voxel is evaluated by the first threads of the block — a few percent of the
+//      points fail, but almost every warp holds one, so without compaction every warp would pay
+//      the second round.
+#pragma once
+#include "lk_async.cuh"
+#include "lk_point.cuh"
+
+namespace lk {
+
+constexpr int TILE_STRIDE = 272;  // 256-byte record + 16: 128-bit reads of 8 consecutive lanes hit 32 banks
+
+template <int NTHREADS>
+struct PassSmem {
+    __align__(16) unsigned char tile[NTHREADS * TILE_STRIDE];
+    struct __align__(8) Fallback {
+        double pc[11];
+        int near;
+        uint32_t idx;
+    } fb[NTHREADS];
+    uint64_t bar[NTHREADS / 32];
+    uint32_t n_fb;
+    uint32_t pad;
+};
+
+struct DebugRows {  // lk_debug_residuals outputs (nullable)
+    uint8_t* ok;
+    double* h;
+    double* z;
+    double* R;
+    int32_t* key;
+};
+
+__device__ __forceinline__ void plane_from_smem(const unsigned char* slot, PlaneRec& r) {
+    const double2* q = reinterpret_cast<const double2*>(slot);
+    double2 v[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) v[i] = q[i];
+    r.c[0] = v[0].x; r.c[1] = v[0].y; r.c[2] = v[1].x;
+    r.n[0] = v[1].y; r.n[1] = v[2].x; r.n[2] = v[2].y;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        r.pv[2 * i] = v[3 + i].x;
+        r.pv[2 * i + 1] = v[3 + i].y;
+    }
+    r.pv[20] = v[13].x;
+    long long dr = __double_as_longlong(v[13].y);
+    r.d = __int_as_float((int)(dr & 0xffffffffll));
+    r.radius = __int_as_float((int)(dr >> 32));
+    long long fc = __double_as_longlong(v[14].x);
+    r.flags = (uint32_t)(fc & 0xffffffffll);
+    r.child_base = (int)(fc >> 32);
+}
+
+__device__ __forceinline__ void accumulate_row(const Row& row, double (&acc)[32]) {
+    const double w = 1.0 / row.R;
+    int q = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const double hw = row.h[r] * w;
+#pragma unroll
+        for (int c = r; c < 6; ++c) acc[q++] += hw * row.h[c];
+        acc[ACC_B + r] += hw * row.z;
+    }
+    acc[ACC_SUMR] += row.R;
+    acc[ACC_CNT] += 1.0;
+}
+
+// Call once per block before the first pass (all threads).
+template <int NTHREADS>
+__device__ __forceinline__ void pass_init(PassSmem<NTHREADS>* ps) {
+    const int tid = threadIdx.x;
+    if ((tid & 31) == 0) mbar_init(&ps->bar[tid >> 5], 1);
+    if (tid == 0) ps->n_fb = 0;
+    mbar_init_fence();
+    __syncthreads();
+}
+
+// Linear probing, two slots per step: an even-aligned pair of 16-byte slots shares one 32-byte
+// sector, so the second slot is free. `pre` holds the pair at the key's home position (already
+// loaded by the caller so several lookups can be in flight together).
+struct SlotPair {
+    int4 a, b;
+};
+__device__ __forceinline__ SlotPair load_pair(const HashSlot* __restrict__ slots, uint32_t i) {
+    SlotPair p;
+    const int4* q = reinterpret_cast<const int4*>(slots + (i & ~1u));
+    p.a = __ldg(q);
+    p.b = __ldg(q + 1);
+    return p;
+}
+__device__ __forceinline__ int resolve_pair(const HashSlot* __restrict__ slots, uint32_t mask, uint32_t i, SlotPair p,
+                                            int kx, int ky, int kz) {
+    // first step may start on the odd slot of its pair
+    if ((i & 1u) == 0) {
+        if (p.a.w < 0) return -1;
+        if (p.a.x == kx && p.a.y == ky && p.a.z == kz) return p.a.w;
+    }
+    if (p.b.w < 0) return -1;
+    if (p.b.x == kx && p.b.y == ky && p.b.z == kz) return p.b.w;
+    uint32_t j = ((i & ~1u) + 2) & mask;
+    for (;;) {
+        p = load_pair(slots, j);
+        if (p.a.w < 0) return -1;
+        if (p.a.x == kx && p.a.y == ky && p.a.z == kz) return p.a.w;
+        if (p.b.w < 0) return -1;
+        if (p.b.x == kx && p.b.y == ky && p.b.z == kz) return p.b.w;
+        j = (j + 2) & mask;
+    }
+}
+
+// What a lane can keep between the iterations of one bucket (fused kernel, one chunk per block):
+// everything that does not depend on the state, plus the last voxel key with its lookup results —
+// when the key is unchanged the probes AND the record gather are skipped (the staged record is
+// still in the lane's tile slot; the map is static within a bucket).
+struct LaneCache {
+    double pbx, pby, pbz, pix, piy, piz, r2, range2;
+    int kx, ky, kz, nx, ny, nz, root, near;
+    int have;  // 0 = nothing cached, 1 = point quantities cached, 2 = + key/root/near/record
+};
+
+// One pass. `phase` is the warp's mbarrier parity (start at 0, carried between passes).
+// base_idx = absolute index of pts[0] (debug output addressing).
+template <int NTHREADS, bool DEBUG, bool CACHED>
+__device__ __forceinline__ void block_points_pass(PassSmem<NTHREADS>* ps, uint32_t& phase, const float4* __restrict__ pts,
+                                                  uint32_t count, size_t base_idx, const ScanConst& sc, const MapView& mv,
+                                                  const Globals& g, double (&acc)[32], const DebugRows& dbg, LaneCache& lc,
+                                                  unsigned long long* tr = nullptr) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#define PT(slot) do { if (tr && (tid & 31) == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); tr[(tid >> 5) * 8 + (slot)] = t_; } } while (0)
+    PT(0);
+    const bool active = (uint32_t)tid < count;
+    PointCtx pc;
+    int root = -1, near = -1;
+    int key[3] = {0, 0, 0};
+    bool need_gather = false;
+    if (active) {
+        if (!CACHED || lc.have == 0) {
+            const float4 pt = __ldg(pts + tid);
+            const double bx = (double)pt.x, by = (double)pt.y, bz = (double)pt.z;
+            pc.pix = g.Re[0] * bx + g.Re[1] * by + g.Re[2] * bz + g.te[0];
+            pc.piy = g.Re[3] * bx + g.Re[4] * by + g.Re[5] * bz + g.te[1];
+            pc.piz = g.Re[6] * bx + g.Re[7] * by + g.Re[8] * bz + g.te[2];
+            // calcBodyCov mutates pb.z AFTER pi / pw were formed (voxel_map.cc:23, KILO.cc:134)
+            pc.pbx = bx; pc.pby = by; pc.pbz = (bz == 0.0) ? 0.0001 : bz;
+            pc.r2 = pc.pbx * pc.pbx + pc.pby * pc.pby + pc.pbz * pc.pbz;
+            const float range = (float)sqrt(pc.r2);
+            pc.range2 = (double)range * (double)range;
+            if (CACHED) {
+                lc.pbx = pc.pbx; lc.pby = pc.pby; lc.pbz = pc.pbz; lc.pix = pc.pix; lc.piy = pc.piy; lc.piz = pc.piz;
+                lc.r2 = pc.r2; lc.range2 = pc.range2;
+                lc.have = 1;
+            }
+        } else {
+            pc.pbx = lc.pbx; pc.pby = lc.pby; pc.pbz = lc.pbz; pc.pix = lc.pix; pc.piy = lc.piy; pc.piz = lc.piz;
+            pc.r2 = lc.r2; pc.range2 = lc.range2;
+        }
+        pc.pwx = sc.R[0] * pc.pix + sc.R[1] * pc.piy + sc.R[2] * pc.piz + sc.p[0];
+        pc.pwy = sc.R[3] * pc.pix + sc.R[4] * pc.piy + sc.R[5] * pc.piz + sc.p[1];
+        pc.pwz = sc.R[6] * pc.pix + sc.R[7] * pc.piy + sc.R[8] * pc.piz + sc.p[2];
+        // voxel key: float quotient, -1 shift for negatives, truncation (KILO.cc:143-148)
+        float lx, ly, lz;
+        if (g.voxel_pow2) {
+            lx = (float)(pc.pwx * g.inv_voxel); ly = (float)(pc.pwy * g.inv_voxel); lz = (float)(pc.pwz * g.inv_voxel);
+        } else {
+            lx = (float)(pc.pwx / g.voxel); ly = (float)(pc.pwy / g.voxel); lz = (float)(pc.pwz / g.voxel);
+        }
+        if (lx < 0) lx = (float)((double)lx - 1.0);
+        if (ly < 0) ly = (float)((double)ly - 1.0);
+        if (lz < 0) lz = (float)((double)lz - 1.0);
+        const int kx = (int)lx, ky = (int)ly, kz = (int)lz;
+        key[0] = kx; key[1] = ky; key[2] = kz;
+        // the neighbour the reference would fall back to: loc in VOXEL units against a centre in
+        // METRES (the reference's own unit mismatch, KILO.cc:158-172)
+        const double q = (double)(g.voxel_f / 4.0f);
+        const double cx = (0.5 + kx) * (double)g.voxel_f, cy = (0.5 + ky) * (double)g.voxel_f, cz = (0.5 + kz) * (double)g.voxel_f;
+        int nx = kx, ny = ky, nz = kz;
+        if ((double)lx > cx + q) nx++; else if ((double)lx < cx - q) nx--;
+        if ((double)ly > cy + q) ny++; else if ((double)ly < cy - q) ny--;
+        if ((double)lz > cz + q) nz++; else if ((double)lz < cz - q) nz--;
+        // NOTE: the neighbour key depends on loc, not only on the home key; it is recomputed and
+        // compared as well before the cache is trusted.
+        if (CACHED && lc.have == 2 && lc.kx == kx && lc.ky == ky && lc.kz == kz ) {
+            root = lc.root;
+            near = lc.near;
+        } else {
+            const bool differs = (nx != kx) || (ny != ky) || (nz != kz);
+            // both home pairs are read before either is inspected
+            const uint32_t ih = hash_key(kx, ky, kz) & mv.hash_mask, in = hash_key(nx, ny, nz) & mv.hash_mask;
+            const SlotPair sh = load_pair(mv.slots, ih);
+            const SlotPair sn = load_pair(mv.slots, in);
+            root = resolve_pair(mv.slots, mv.hash_mask, ih, sh, kx, ky, kz);
+            // the reference only looks at the neighbour when the home voxel exists
+            near = (root >= 0 && differs) ? resolve_pair(mv.slots, mv.hash_mask, in, sn, nx, ny, nz) : -1;
+            need_gather = root >= 0;
+        }
+        if (CACHED) {
+            // the cached `near` is only valid for the same neighbour key; remember it alongside
+            if (lc.have == 2 && lc.kx == kx && lc.ky == ky && lc.kz == kz && (lc.nx != nx || lc.ny != ny || lc.nz != nz)) {
+                // same home voxel, different neighbour: redo the neighbour lookup only
+                const bool differs = (nx != kx) || (ny != ky) || (nz != kz);
+                const uint32_t in = hash_key(nx, ny, nz) & mv.hash_mask;
+                near = (root >= 0 && differs) ? resolve_pair(mv.slots, mv.hash_mask, in, load_pair(mv.slots, in), nx, ny, nz) : -1;
+            }
+            lc.kx = kx; lc.ky = ky; lc.kz = kz; lc.nx = nx; lc.ny = ny; lc.nz = nz;
+            lc.root = root; lc.near = near;
+            lc.have = 2;
+        }
+    }
+    PT(1);
+    // ---- stage the home records: one bulk copy per lane -------------------------------------------
+    unsigned char* my_slot = ps->tile + (size_t)tid * TILE_STRIDE;
+    const bool gather = CACHED ? need_gather : (root >= 0);
+    const uint32_t valid = __ballot_sync(0xffffffffu, gather);
+    if (valid) {
+        if (lane == 0) mbar_expect_tx(&ps->bar[warp], 256u * (uint32_t)__popc(valid));
+        __syncwarp();
+        if (gather) bulk_g2s(my_slot, mv.nodes + root, 256u, &ps->bar[warp]);
+        mbar_wait(&ps->bar[warp], phase);
+        phase ^= 1u;
+    }
+    PT(2);
+    // ---- gates + row -----------------------------------------------------------------------------
+    Row row;
+    bool ok = false;
+    double prob = 0.0;
+    if (root >= 0) {
+        PlaneRec r;
+        plane_from_smem(my_slot, r);
+        if (r.flags & LK_NODE_IS_PLANE) {
+            ok = eval_plane(r, pc, sc, g, false, prob, row);
+        } else {
+            const uint32_t cmask = (r.flags >> LK_NODE_CHILDMASK_SHIFT) & 0xffu;
+            if (g.max_layer >= 1 && r.child_base >= 0 && cmask)
+                ok = visit_subtree(mv.nodes, r.child_base, cmask, &pc, &sc, &g, &prob, &row);
+        }
+        if (!ok && near >= 0) {
+            const uint32_t slot = atomicAdd(&ps->n_fb, 1u);
+            typename PassSmem<NTHREADS>::Fallback& f = ps->fb[slot];
+            f.pc[0] = pc.pbx; f.pc[1] = pc.pby; f.pc[2] = pc.pbz; f.pc[3] = pc.pix; f.pc[4] = pc.piy; f.pc[5] = pc.piz;
+            f.pc[6] = pc.pwx; f.pc[7] = pc.pwy; f.pc[8] = pc.pwz; f.pc[9] = pc.r2; f.pc[10] = pc.range2;
+            f.near = near;
+            f.idx = (uint32_t)tid;
+        }
+    }
+    PT(3);
+    if (DEBUG) {
+        if (active) {
+            const size_t gi = base_idx + tid;
+            dbg.ok[gi] = ok ? 1 : 0;
+            for (int k = 0; k < 3; ++k) dbg.key[gi * 3 + k] = key[k];
+            for (int k = 0; k < 6; ++k) dbg.h[gi * 6 + k] = ok ? row.h[k] : 0.0;
+            dbg.z[gi] = ok ? row.z : 0.0;
+            dbg.R[gi] = ok ? row.R : 0.0;
+        }
+    }
+    __syncthreads();
+    PT(4);
+    // ---- fallback round: the neighbour voxel of the points that failed at home ------------------------
+    const uint32_t n_fb = ps->n_fb;
+    Row row2;
+    bool ok2 = false;
+    if ((uint32_t)tid < n_fb) {
+        const typename PassSmem<NTHREADS>::Fallback& f = ps->fb[tid];
+        PointCtx fc;
+        fc.pbx = f.pc[0]; fc.pby = f.pc[1]; fc.pbz = f.pc[2]; fc.pix = f.pc[3]; fc.piy = f.pc[4]; fc.piz = f.pc[5];
+        fc.pwx = f.pc[6]; fc.pwy = f.pc[7]; fc.pwz = f.pc[8]; fc.r2 = f.pc[9]; fc.range2 = f.pc[10];
+        PlaneRec r;
+        load_plane(mv.nodes + f.near, r);
+        double prob2 = 0.0;
+        if (r.flags & LK_NODE_IS_PLANE) {
+            ok2 = eval_plane(r, fc, sc, g, false, prob2, row2);
+        } else {
+            const uint32_t cmask = (r.flags >> LK_NODE_CHILDMASK_SHIFT) & 0xffu;
+            if (g.max_layer >= 1 && r.child_base >= 0 && cmask)
+                ok2 = visit_subtree(mv.nodes, r.child_base, cmask, &fc, &sc, &g, &prob2, &row2);
+        }
+        if (ok2) {
+            if (DEBUG) {
+                const size_t gi = base_idx + f.idx;
+                dbg.ok[gi] = 1;
+                for (int k = 0; k < 6; ++k) dbg.h[gi * 6 + k] = row2.h[k];
+                dbg.z[gi] = row2.z;
+                dbg.R[gi] = row2.R;
+            }
+        }
+    }
+    PT(5);
+    if (!DEBUG) {  // rows are folded in only now, so no accumulator is live across the evaluations
+        if (ok) accumulate_row(row, acc);
+        if (ok2) accumulate_row(row2, acc);
+    }
+    PT(6);
+    __syncthreads();
+    if (tid == 0) ps->n_fb = 0;
+    PT(7);
+#undef PT
+}
+
+}  // namespace lk

@@ -8,6 +8,7 @@
 // symmetric eigenproblem (Jacobi), and the 6x6 plane covariance is accumulated lane-parallel over
 // the tile and shuffle-reduced.
 #pragma once
+#include "lk_async.cuh"
 #include "lk_device.cuh"
 
 namespace lk {
@@ -33,34 +34,6 @@ struct MapDev {
 };
 
 constexpr int TILE_PTS = 64;  // points per staged tile (5 120 B)
-
-// ---- mbarrier / bulk-copy primitives (PTX) ----------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "LK_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra LK_DONE_%=;\n\t"
-        "bra LK_WAIT_%=;\n\t"
-        "LK_DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// 1-D TMA bulk copy global -> shared::cta; size multiple of 16, both addresses 16-B aligned.
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- 3x3 symmetric eigen-decomposition (cyclic Jacobi), every lane redundantly -----------------
 // C = {xx, xy, xz, yy, yz, zz}; returns eigenvalues w[3] and unit eigenvectors as columns of V.

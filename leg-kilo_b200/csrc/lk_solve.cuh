@@ -1,0 +1,155 @@
+// lk_solve.cuh — block-level pieces of ESKF::updateByPoints (eskf.cc:91-113) in information form,
+// operating on a filter (state 36 + covariance 900 doubles) held in shared memory:
+//   K = P H^T (H P H^T + R)^-1  ==  P[:,0:6] (I + A P66)^-1,  A = sum h^T h / R, b = sum h^T z / R
+// (SURVEY §8a a8, Appendix A.5), followed by State::operator+= (eskf.cc:18-29) and, on the last
+// iteration, P <- P - K H P[0:6,:] (no symmetrisation, as the reference).
+#pragma once
+#include "lk_point.cuh"
+
+namespace lk {
+
+struct BlockFilter {
+    double x[36];
+    double P[900];
+    double acc[32];   // reduced A (21) | b (6) | sumR | count
+    double A[36];
+    double M[36];
+    double y[6];
+    double W[36];
+    double delta[30];
+    double Prow[180];
+    double KH[180];
+};
+
+// Deterministic sum of per-chunk partial rows [c0, c1): warp w takes rows w, w+nw, ... (all loads
+// of a warp issued before the first add), then the per-warp slices are added in fixed order.
+// `slice` must hold nwarps*32 doubles. Result in out[0..31]. All threads of the block call.
+template <int NWARPS>
+__device__ __forceinline__ void block_sum_partials(const double* partial, uint32_t c0, uint32_t c1, double* slice,
+                                                   double* out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double acc = 0.0;
+    uint32_t c = c0 + warp;
+    for (; c + 7 * NWARPS < c1; c += 8 * NWARPS) {
+        const double* p = partial + (size_t)c * PARTIAL_STRIDE + lane;
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(p + (size_t)u * NWARPS * PARTIAL_STRIDE);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    {
+        const double* p = partial + (size_t)c * PARTIAL_STRIDE + lane;
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (c + u * NWARPS < c1) ? __ldcg(p + (size_t)u * NWARPS * PARTIAL_STRIDE) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (c + u * NWARPS < c1) acc += v[u];
+    }
+    slice[warp * 32 + lane] = acc;
+    __syncthreads();
+    if (tid < 32) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) v += slice[w * 32 + tid];
+        out[tid] = v;
+    }
+    __syncthreads();
+}
+
+// The update itself. f->acc holds the reduced sums. Returns the residual count. All threads call.
+// Warp 0 carries the whole serial chain (A, M = I + A P66, Gauss-Jordan, delta, State (+)) with
+// warp-level synchronisation only; the block joins for the covariance update of the last iteration.
+template <int NTHREADS>
+__device__ __forceinline__ uint32_t block_solve_update(BlockFilter* f, bool last_iter) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double cnt = f->acc[ACC_CNT];
+    if (cnt > 0.5) {
+        if (warp == 0) {
+            // N == 1 adds 1e-4 to S (eskf.cc:100)  <=>  weights scale by R / (R + 1e-4)
+            const double scale = (cnt < 1.5) ? f->acc[ACC_SUMR] / (f->acc[ACC_SUMR] + 0.0001) : 1.0;
+            for (int e = lane; e < 36; e += 32) {
+                int i = e / 6, j = e % 6;
+                int r = i < j ? i : j, c = i < j ? j : i;
+                f->A[e] = f->acc[r * 6 - r * (r - 1) / 2 + (c - r)] * scale;
+            }
+            __syncwarp();
+            double col[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                double v = 0.0;
+                if (lane < 6) {  // column `lane` of M = I + A P66
+                    v = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) v += f->A[i * 6 + k] * f->P[k * 30 + lane];
+                } else if (lane == 6) v = f->acc[ACC_B + i] * scale;
+                else if (lane < 13) v = f->A[i * 6 + (lane - 7)];
+                col[i] = v;
+            }
+            const bool okl = warp_solve6(col, lane);
+            double y[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                y[i] = __shfl_sync(0xffffffffu, okl ? col[i] : 0.0, 6);
+                if (lane >= 7 && lane < 13) f->W[i * 6 + (lane - 7)] = okl ? col[i] : 0.0;
+            }
+            double d = 0.0;
+            if (lane < 30) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) d += f->P[lane * 30 + k] * y[k];
+            }
+            // State::operator+= : Exp(delta_theta) is formed by every lane from the broadcast angles
+            const double d0 = __shfl_sync(0xffffffffu, d, 0), d1 = __shfl_sync(0xffffffffu, d, 1),
+                         d2 = __shfl_sync(0xffffffffu, d, 2);
+            double rv = 0.0;
+            if (lane < 9) {
+                double E[9];
+                so3_exp3(d0, d1, d2, E);
+                const int i = lane / 3, j = lane % 3;
+                rv = f->x[i * 3] * E[j] + f->x[i * 3 + 1] * E[3 + j] + f->x[i * 3 + 2] * E[6 + j];
+            }
+            __syncwarp();
+            if (lane < 9) f->x[lane] = rv;
+            if (lane >= 3 && lane < 30) f->x[6 + lane] += d;  // delta[3..29] -> x[9..35]
+        }
+        __syncthreads();
+        if (last_iter) {
+            // P <- P - (P6 W) P[0:6,:]   (eskf.cc:112, no symmetrisation)
+            for (int e = tid; e < 180; e += NTHREADS) {
+                f->Prow[e] = f->P[e];  // rows 0..5 are contiguous
+                int i = e / 6, j = e % 6;
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) s += f->P[i * 30 + k] * f->W[k * 6 + j];
+                f->KH[e] = s;
+            }
+            __syncthreads();
+            for (int e = tid; e < 900; e += NTHREADS) {
+                int i = e / 30, j = e % 30;
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) s += f->KH[i * 6 + k] * f->Prow[k * 30 + j];
+                f->P[e] -= s;
+            }
+            __syncthreads();
+        }
+    }
+    return (uint32_t)(cnt + 0.5);
+}
+
+// ScanConst from a shared-memory filter. Threads 0..23.
+__device__ __forceinline__ void scan_const_from(const BlockFilter* f, ScanConst* sc) {
+    const int tid = threadIdx.x;
+    if (tid < 9) sc->R[tid] = f->x[tid];
+    else if (tid < 12) sc->p[tid - 9] = f->x[tid];
+    else if (tid < 24) {
+        const int ut[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+        const int q = (tid - 12) % 6, o = (tid < 18) ? 0 : 3;
+        const int i = ut[q][0] + o, j = ut[q][1] + o;
+        const double v = 0.5 * (f->P[i * 30 + j] + f->P[j * 30 + i]);
+        if (tid < 18) sc->Pth[q] = v; else sc->Ppp[q] = v;
+    }
+}
+
+}  // namespace lk

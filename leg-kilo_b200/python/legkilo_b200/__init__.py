@@ -54,6 +54,10 @@ def lib():
         L.lk_scan_update.argtypes = [vp, i32] + [vp] * 9 + [i32, i32, vp, vp]
         L.lk_batch_stage.argtypes = [vp, i32] + [vp] * 9
         L.lk_batch_run.argtypes = [vp, i32, i32]
+        L.lk_batch_run_range.argtypes = [vp, u32, u32, i32, i32]
+        L.lk_timer_start.argtypes = [vp]
+        L.lk_timer_stop.argtypes = [vp] * 5
+        L.lk_debug_read.argtypes = [vp, i32, vp, C.c_size_t]
         L.lk_batch_fetch.argtypes = [vp] * 6
         L.lk_batch_last_timing.argtypes = [vp] * 5
         L.lk_debug_residuals.argtypes = [vp, vp, vp, vp, u32] + [vp] * 5
@@ -206,6 +210,21 @@ class Engine:
 
     def run(self, iters=1, update_map=False):
         self._chk(lib().lk_batch_run(self.h, iters, int(update_map)))
+
+    def run_range(self, first, count, iters=1, update_map=False):
+        """Asynchronous: enqueue scans [first, first+count) of the staged batch (no host sync)."""
+        self._chk(lib().lk_batch_run_range(self.h, first, count, iters, int(update_map)))
+
+    def timer_start(self):
+        self._chk(lib().lk_timer_start(self.h))
+
+    def timer_stop(self):
+        t = C.c_float(); r = C.c_float(); n = C.c_uint32(); nr = C.c_uint32()
+        self._chk(lib().lk_timer_stop(self.h, C.byref(t), C.byref(r), C.byref(n), C.byref(nr)))
+        return dict(total_ms=t.value, residual_ms=r.value, launches=n.value, residual_launches=nr.value)
+
+    def sync(self):
+        self._chk(lib().lk_sync(self.h))
 
     def fetch(self, want_world=True):
         batch, npts = self._staged

@@ -93,12 +93,21 @@ class BoxScene:
     Plane offsets sit mid-voxel (…25) so that noisy samples stay inside one root voxel."""
 
     def __init__(self, ground_half_extent: float = 250.0, wall: float = 15.25, zg: float = -0.75, z_top: float = 6.25,
-                 voxel: float = 0.5):
+                 voxel: float = 0.5, rooms=None):
         self.E = float(ground_half_extent)
         self.W = float(wall)
         self.zg = float(zg)
         self.z_top = float(z_top)
         self.voxel = float(voxel)
+        # room centres (multiples of the voxel size so every room looks the same on the voxel grid)
+        self.rooms = [(0.0, 0.0)] if rooms is None else [(float(a), float(b)) for a, b in rooms]
+
+    @staticmethod
+    def room_grid(n_side: int, spacing: float = 62.0):
+        """n_side x n_side room centres, `spacing` metres apart, centred on the origin."""
+        c = (np.arange(n_side) - (n_side - 1) / 2.0) * spacing
+        c = np.round(c / 0.5) * 0.5
+        return [(float(a), float(b)) for a in c for b in c]
 
     # -- first-frame style dense cloud for the map --------------------------------------------
     def map_points(self, pts_per_voxel: int = 8, sigma: float = 0.01, ext_R=None, ext_t=None, stream: int = 11,
@@ -123,33 +132,47 @@ class BoxScene:
         il, ih = np.meshgrid(np.arange(nl), np.arange(nh), indexing="ij")
         cell = np.stack([il.ravel(), ih.ravel()], 1).astype(np.float64)
         cell = np.repeat(cell, pts_per_voxel, axis=0)
-        for axis, sign in ((0, 1), (0, -1), (1, 1), (1, -1)):
-            u = cell + g.uniform(0.04, 0.96, size=cell.shape)
-            along = -self.W - 0.25 + u[:, 0] * v
-            hz = np.floor(self.zg / v) * v + u[:, 1] * v
-            off = sign * self.W + sigma * g.standard_normal(len(u))
-            ok = (np.abs(along) < self.W) & (hz > self.zg + 0.05) & (hz < self.z_top)
-            p = np.zeros((ok.sum(), 3))
-            p[:, axis] = off[ok]
-            p[:, 1 - axis] = along[ok]
-            p[:, 2] = hz[ok]
-            chunks.append(p)
+        for (rcx, rcy) in self.rooms:
+            rc = (rcx, rcy)
+            for axis, sign in ((0, 1), (0, -1), (1, 1), (1, -1)):
+                u = cell + g.uniform(0.04, 0.96, size=cell.shape)
+                along = -self.W - 0.25 + u[:, 0] * v
+                hz = np.floor(self.zg / v) * v + u[:, 1] * v
+                off = sign * self.W + sigma * g.standard_normal(len(u))
+                ok = (np.abs(along) < self.W) & (hz > self.zg + 0.05) & (hz < self.z_top)
+                p = np.zeros((ok.sum(), 3))
+                p[:, axis] = rc[axis] + off[ok]
+                p[:, 1 - axis] = rc[1 - axis] + along[ok]
+                p[:, 2] = hz[ok]
+                chunks.append(p)
         pw = np.concatenate(chunks, 0)
-        pb = world_to_body(pw, np.eye(3), np.zeros(3), ext_R, ext_t)
+        # every point is "seen" from the centre of its nearest room (identity attitude), the way a
+        # first frame taken there would see it: body = ext^-1 (world - room centre)
+        rc = np.asarray(self.rooms, float)
+        near = np.zeros(len(pw), np.int64)
+        best = np.full(len(pw), np.inf)
+        for i, c in enumerate(rc):
+            d2 = (pw[:, 0] - c[0]) ** 2 + (pw[:, 1] - c[1]) ** 2
+            m = d2 < best
+            near[m] = i
+            best[m] = d2[m]
+        origin = np.concatenate([rc[near], np.zeros((len(pw), 1))], 1)
+        pb = world_to_body(pw - origin, np.eye(3), np.zeros(3), ext_R, ext_t)
         pb32 = pb.astype(np.float32)
-        pw32 = ((pb32.astype(np.float64) @ ext_R.T) + ext_t).astype(np.float32)
+        pw32 = (((pb32.astype(np.float64) @ ext_R.T) + ext_t) + origin).astype(np.float32)
         return pw32, pb32
 
     # -- one LiDAR revolution -------------------------------------------------------------------
     def scan(self, n_rings: int, n_az: int, fov_deg: tuple[float, float], rotvec, trans, ext_R=None, ext_t=None,
              sigma: float = 0.01, blind: float = 1.5, stream: int = 21, scan_period: float = 0.1,
-             time_quantum: float = 0.002, streaming: bool = False, sensor_xy=(0.0, 0.0)):
+             time_quantum: float = 0.002, streaming: bool = False, room: int = 0):
         """Ray-cast n_rings x n_az rays from the true pose. Returns float32 [n,4]; curvature is
         the 2 ms-quantised time offset (lidar_processing.cc:48) when streaming, else 0."""
         ext_R = np.eye(3) if ext_R is None else np.asarray(ext_R, float)
         ext_t = np.zeros(3) if ext_t is None else np.asarray(ext_t, float)
         g = rng(stream)
         R = exp_so3(rotvec)
+        sensor_xy = self.rooms[room]
         p = np.asarray(trans, float) + np.array([sensor_xy[0], sensor_xy[1], 0.0])
         el = np.deg2rad(np.linspace(fov_deg[0], fov_deg[1], n_rings))
         az = (np.arange(n_az) + 0.5) * (2 * np.pi / n_az)

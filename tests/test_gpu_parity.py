@@ -68,3 +68,25 @@ def test_box_room_batch(iters):
         assert int(out["n_eff"][i]) == ro["n_eff"] > 0
         assert scenes.rel_state_err(out["x"][i:i + 1], xo, x0[i:i + 1]) < TOL
         assert scenes.rel_cov_err(out["P"][i], Po) < TOL
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_single_scan_paths_agree_with_oracle(fused):
+    """batch = 1 runs go through the persistent per-scan kernel (fused=1) or the multi-kernel path
+    (fused=0); both must match the oracle and — same arithmetic, same order — each other bitwise."""
+    cfg, blob, scans = scenes.box_scene(batch=1, stream0=300)
+    eng = Engine(cfg)
+    eng.set_param("fused", fused)
+    eng.map_upload(blob)
+    x0 = abi.default_states(1); P0 = abi.init_cov(1)
+    out = eng.scan_update(x0, P0, abi.process_cov_Q(cfg), np.zeros(1, abi.CLOCK_DTYPE), scans[0], [0, len(scans[0])], [0.0], iters=3)
+    ro, xo, Po, _ = _oracle_bucket(cfg, blob, scans[0], x0, P0, iters=3)
+    assert int(out["n_eff"][0]) == ro["n_eff"] > 0
+    assert scenes.rel_state_err(out["x"], xo, x0) < TOL
+    assert scenes.rel_cov_err(out["P"][0], Po) < TOL
+    np.testing.assert_allclose(out["world"][:, :3], ro["world"][:, :3], rtol=0, atol=2e-6)
+    key = "_single_scan_ref"
+    if key in globals():
+        np.testing.assert_array_equal(globals()[key]["x"].view(np.float64), out["x"].view(np.float64))
+        np.testing.assert_array_equal(globals()[key]["P"], out["P"])
+    globals()[key] = out
