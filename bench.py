@@ -36,6 +36,8 @@ WORKLOADS = {
                           baseline_config="configs[1]: leg_fusion 16-line ~28.8k pts/scan, 3 iters, ~1M-voxel map, batch=1"),
     "diter_b128": dict(cfg="diter", lidar="OS64", iters=3, batch=128, ring=128, half=250.0, rooms=8,
                        baseline_config="configs[2]: Diter++ OS-64 ~131k pts/scan, 3 iters, batch=128"),
+    "diter_b16": dict(cfg="diter", lidar="OS64", iters=3, batch=16, ring=16, half=60.0, rooms=1,
+                      baseline_config="profiling-size variant of configs[2]"),
     "small": dict(cfg="leg_fusion", lidar="VLP16", iters=3, batch=1, ring=16, half=40.0, rooms=1,
                   baseline_config="smoke-size variant of configs[1]"),
 }
@@ -270,7 +272,8 @@ def main():
     res_ms = tm["residual_ms"] / r_launches
     alg_bytes_per_launch = ALG_BYTES_PER_POINT_ITER * (work / r_launches)
     achieved = alg_bytes_per_launch / (res_ms * 1e-3) / 1e9 if res_ms > 0 else 0.0
-    roofline = dict(bound="hbm", kernel="k_residual", achieved=achieved, peak=hbm_peak, unit="GB/s",
+    fused = (B == 1 and args.fused != 0)
+    roofline = dict(bound="hbm", kernel="k_scan_fused (whole scan: 3 x [residual+reduce+solve] + re-projection)" if fused else "k_residual", achieved=achieved, peak=hbm_peak, unit="GB/s",
                     frac=achieved / hbm_peak, traffic=None, peak_source=peak_src,
                     alg_bytes_per_launch=alg_bytes_per_launch, avg_launch_us=res_ms * 1e3,
                     share_of_step=tm["residual_ms"] / tm["total_ms"] if tm["total_ms"] > 0 else None)

@@ -64,6 +64,7 @@ struct lk_context {
     DevBuf pts, world, chunks, stepinit, x_in, P_in, clk_in, Q, x, P, clk, sc, step, partial, ticket, n_eff;
     DevBuf dbg_ok, dbg_h, dbg_z, dbg_R, dbg_key, tmp, trace, bar;
     int trace_on = 0;
+    int lane_cache = 1;
     int use_fused = 1;      // batch-of-one runs go through the persistent per-scan kernel
     int fused_parity = 0;
     uint32_t fused_launches = 0;
@@ -266,6 +267,7 @@ int lk_set_param(lk_handle h, const char* name, double value) {
     if (!std::strcmp(name, "gather_mode")) { h->gather_mode = (int)value; return LK_OK; }
     if (!std::strcmp(name, "kernel_timing")) { h->kernel_timing = (int)value; return LK_OK; }
     if (!std::strcmp(name, "fused")) { h->use_fused = (int)value; return LK_OK; }
+    if (!std::strcmp(name, "lane_cache")) { h->lane_cache = (int)value; return LK_OK; }
     if (!std::strcmp(name, "trace")) {
         h->trace_on = (int)value;
         if (h->trace_on) {
@@ -523,6 +525,7 @@ int lk_batch_run_range(lk_handle h, uint32_t first, uint32_t count, int iters, i
         fa.parity = h->fused_parity;
         h->fused_parity ^= 1;
         fa.iters = iters;
+        fa.lane_cache = h->lane_cache;
         fa.mv.slots = h->map.slots;
         fa.mv.hash_mask = (uint32_t)(h->map.hash_cap - 1);
         fa.mv.nodes = h->map.nodes;
@@ -561,7 +564,7 @@ int lk_batch_run_range(lk_handle h, uint32_t first, uint32_t count, int iters, i
             ra.chunk_first = c0;
             ra.last_iter = (it == iters - 1) ? 1 : 0;
             if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
-            launch_residual(ra, c1 - c0, false, h->max_chunk_pts <= 256, s);
+            launch_residual(ra, c1 - c0, false, h->max_chunk_pts <= 256 && (c1 - c0) <= 2 * 148, s);  // latency variant only for small grids
             if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
             if (c1 > c0) { ++h->acc_launches; ++h->acc_residual_launches; }
         }

@@ -43,6 +43,8 @@ struct FusedSmem {
     } u;
 };
 
+static_assert(sizeof(PredictScratch) <= sizeof(((PassSmem<BLOCK>*)0)->tile), "predict scratch must not reach the mbarriers");
+
 __device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t target) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -89,8 +91,10 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
         if (dtc != 0.0) {
             build_F(sm->u.pr.F, sm->f.x, dtc);
             cov_predict(sm->f.P, sm->u.pr.F, sm->u.pr.T, sm->u.pr.Ps, a.Q, dtc);
-            pass_init<BLOCK>(&sm->u.pass);  // the scratch aliased the pass area
-            phase = 0;
+            // the scratch aliased the record tile (not the mbarriers, which sit behind it and keep
+            // their phases): order these generic-proxy writes before the next bulk copies
+            fence_proxy_async();
+            __syncthreads();
         }
         if (dt != 0.0) {
             if (tid == 0) state_predict(sm->f.x, dt);
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
         bool updated = false;
         uint32_t n_last = 0;
         // with one chunk per block a lane sees the same point in every iteration of the bucket
-        const bool one_chunk = (in.chunk_end - in.chunk_begin) <= gridDim.x;
+        const bool one_chunk = a.lane_cache && (in.chunk_end - in.chunk_begin) <= gridDim.x;
         LaneCache lc;
         lc.have = 0;
         const uint32_t n_chunks = in.chunk_end - in.chunk_begin;

@@ -102,6 +102,7 @@ struct FusedArgs {
     uint32_t* bar;  // [2] grid-barrier counters, used alternately by consecutive launches
     int parity;
     int iters;
+    int lane_cache;  // keep per-lane lookups / staged records across the iterations of a bucket
     MapView mv;
     unsigned long long* trace;  // optional: 32 %globaltimer stamps per block
     Globals g;

@@ -143,6 +143,7 @@ void launch_residual(const ResidualArgs& a, uint32_t n_chunks, bool debug, bool 
         cudaFuncSetAttribute(k_residual<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_residual<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_residual<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_residual<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         attr_set = true;
     }
     if (debug)

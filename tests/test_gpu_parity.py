@@ -6,7 +6,7 @@ import pytest
 
 import lko
 import scenes
-from legkilo_b200 import Engine, abi
+from legkilo_b200 import Engine, abi, synth
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -90,3 +90,50 @@ def test_single_scan_paths_agree_with_oracle(fused):
         np.testing.assert_array_equal(globals()[key]["x"].view(np.float64), out["x"].view(np.float64))
         np.testing.assert_array_equal(globals()[key]["P"], out["P"])
     globals()[key] = out
+
+
+def _oracle_stream(cfg, blob, pts_sorted, begin_time, x0, P0, clk0, iters=1, update_map=False, gain=lko.GAIN_INFORMATION,
+                   imu=None, kin=None, imu_mode_only=True):
+    o = lko.Oracle(cfg)
+    o.map_import(blob)
+    o.set_filter(x0, P0, abi.process_cov_Q(cfg), clk0)
+    o.set_options(gain_mode=gain, iters=iters, update_map=update_map, imu_mode_only=imu_mode_only)
+    r = o.process_scan(begin_time, pts_sorted, imu=imu, kin=kin)
+    x, P, _, clk = o.get_filter()
+    return r, x, P, clk, o
+
+
+def _moving_state():
+    """A prior with non-trivial velocity / angular rate / acceleration so that predict matters."""
+    x0 = abi.default_states(1)
+    x0["vel"][0] = (0.4, -0.2, 0.05)
+    x0["imu_w"][0] = (0.02, -0.03, 0.15)
+    x0["imu_a"][0] = (0.3, 0.1, 9.7)
+    x0["ba"][0] = (0.01, -0.02, 0.03)
+    x0["bw"][0] = (1e-3, 2e-3, -1e-3)
+    return x0
+
+
+@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("iters", [1, 2])
+def test_streaming_buckets_static_map(fused, iters):
+    """~50 time buckets per scan (2 ms quantisation): predict (eskf.cc:83-89) -> residuals -> update per
+    bucket, map static. Exercises rows a1, a2, a8, a9, a10 through both device paths."""
+    cfg, blob, scans = scenes.box_scene(batch=1, streaming=True, stream0=500)
+    pts, offs, times = synth.bucketize(scans[0], begin_time=100.0)
+    assert len(times) > 30
+    x0 = _moving_state(); P0 = abi.init_cov(1)
+    clk0 = np.zeros(1, abi.CLOCK_DTYPE); clk0["last_predict_time"] = 99.99; clk0["last_update_time"] = 99.985
+    ro, xo, Po, clko, _ = _oracle_stream(cfg, blob, pts, 100.0, x0, P0, clk0, iters=iters)
+    eng = Engine(cfg)
+    eng.set_param("fused", fused)
+    eng.map_upload(blob)
+    out = eng.scan_update(x0, P0, abi.process_cov_Q(cfg), clk0, pts, [0, len(pts)], times, scan_bucket_ptr=[0, len(times)],
+                          bucket_offsets=offs, iters=iters)
+    assert int(out["n_eff"][0]) == ro["n_eff"] > 0
+    assert scenes.rel_state_err(out["x"], xo, x0) < TOL
+    assert scenes.rel_cov_err(out["P"][0], Po) < TOL
+    assert out["clk"]["last_predict_time"][0] == clko["last_predict_time"][0]
+    assert out["clk"]["last_update_time"][0] == clko["last_update_time"][0]
+    np.testing.assert_allclose(out["world"][:, :3], ro["world"][:, :3], rtol=0, atol=5e-6)
+    np.testing.assert_array_equal(out["world"][:, 3], ro["world"][:, 3])
