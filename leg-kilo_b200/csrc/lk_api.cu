@@ -63,6 +63,8 @@ struct lk_context {
     std::vector<uint32_t> step_chunk_ptr;
     DevBuf pts, world, chunks, stepinit, x_in, P_in, clk_in, Q, x, P, clk, sc, step, partial, ticket, n_eff;
     DevBuf dbg_ok, dbg_h, dbg_z, dbg_R, dbg_key, tmp, trace, bar;
+    DevBuf ins_pts, ins_root, ins_pend, ins_touched, ins_counters, ins_list;
+    uint64_t ins_pend_nodes = 0;
     int trace_on = 0;
     int lane_cache = 1;
     int use_fused = 1;      // batch-of-one runs go through the persistent per-scan kernel
@@ -78,6 +80,7 @@ struct lk_context {
     size_t nev = 0;
     int kernel_timing = 1;
     std::vector<StepInit> h_inits;
+    std::vector<uint32_t> h_scan_pts;
 };
 
 namespace {
@@ -218,7 +221,8 @@ int lk_destroy(lk_handle h) {
     DevBuf* bufs[] = {&h->pts, &h->world,
                       &h->chunks, &h->stepinit, &h->x_in, &h->P_in, &h->clk_in, &h->Q, &h->x, &h->P, &h->clk, &h->sc,
                       &h->step, &h->partial, &h->ticket, &h->n_eff, &h->dbg_ok, &h->dbg_h, &h->dbg_z, &h->dbg_R,
-                      &h->dbg_key, &h->tmp, &h->trace, &h->bar};
+                      &h->dbg_key, &h->tmp, &h->trace, &h->bar, &h->ins_pts, &h->ins_root, &h->ins_pend, &h->ins_touched,
+                      &h->ins_counters, &h->ins_list};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : h->kev) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -411,6 +415,8 @@ int lk_batch_stage(lk_handle h, int batch, const lk_state* x, const double* P, c
     }
     h->step_chunk_ptr[max_buckets] = (uint32_t)chunks.size();
     h->batch = batch;
+    h->h_scan_pts.assign(batch, 0);
+    for (int s2 = 0; s2 < batch; ++s2) h->h_scan_pts[s2] = scan_offsets[s2 + 1] - scan_offsets[s2];
     h->total_pts = total;
     h->total_chunks = (uint32_t)chunks.size();
     h->max_chunk_pts = 0;
@@ -489,12 +495,38 @@ int lk_batch_run_range(lk_handle h, uint32_t first, uint32_t count, int iters, i
     if (h->batch <= 0) return fail(h, LK_ERR_NOT_READY, "lk_batch_run before lk_batch_stage");
     if (iters < 1) return fail(h, LK_ERR_INVALID_ARG, "iters must be >= 1");
     if (count == 0 || first + count > (uint32_t)h->batch) return fail(h, LK_ERR_INVALID_ARG, "scan range outside the staged batch");
-    if (update_map) return fail(h, LK_ERR_NOT_READY, "update_map: device-side UpdateVoxelMap not available in this build");
-    if (!h->map.ready()) return fail(h, LK_ERR_NOT_READY, "no map: call lk_map_upload or lk_map_build first");
+    if (update_map && count != 1)
+        return fail(h, LK_ERR_INVALID_ARG, "update_map inserts into this handle's map: run one scan (stream) per call");
     cudaSetDevice(h->device);
     cudaStream_t s = h->stream;
     const int batch = h->batch;
-    if (count == 1 && h->use_fused && h->max_chunk_pts <= 256) {
+    uint32_t max_bucket = 0;
+    if (update_map) {
+        // UpdateVoxelMap may create the map: make room for this scan's points (roots, nodes, tiles)
+        const uint64_t n = h->h_scan_pts[first];
+        std::string err;
+        int rc = h->map.ready() ? h->map.sync_counters(s, err) : LK_OK;
+        if (!rc) rc = h->map.ensure_headroom(n + 16, 4 * n + 64, 60 * n + 64, s, err);
+        if (!rc) rc = h->map.push_counters(s, err);
+        if (rc) return fail(h, rc, err);
+        for (uint32_t k = 0; k < h->n_steps; ++k) {
+            const StepInit& in = h->h_inits[(size_t)k * batch + first];
+            max_bucket = std::max(max_bucket, in.pt_end - in.pt_begin);
+        }
+        const size_t mb = std::max<size_t>(max_bucket, 1);
+        LK_CUDA(h, h->ins_pts.ensure(mb * insert_point_bytes()));
+        LK_CUDA(h, h->ins_root.ensure(mb * 4));
+        LK_CUDA(h, h->ins_touched.ensure(mb * 4));
+        LK_CUDA(h, h->ins_list.ensure(2 * mb * 4));
+        LK_CUDA(h, h->ins_counters.ensure(64));
+        if (h->ins_pend_nodes < h->map.node_cap) {
+            LK_CUDA(h, h->ins_pend.ensure((size_t)h->map.node_cap * 12));
+            LK_CUDA(h, cudaMemsetAsync(h->ins_pend.p, 0, h->ins_pend.cap, s));
+            h->ins_pend_nodes = h->map.node_cap;
+        }
+    }
+    if (!h->map.ready()) return fail(h, LK_ERR_NOT_READY, "no map: call lk_map_upload or lk_map_build first");
+    if (count == 1 && h->use_fused && h->max_chunk_pts <= 256 && !update_map) {
         // one scan: the whole bucket loop in ONE persistent cooperative kernel (lk_fused.cu)
         uint32_t max_chunks = 1;
         for (uint32_t k = 0; k < h->n_steps; ++k) {
@@ -578,8 +610,24 @@ int lk_batch_run_range(lk_handle h, uint32_t first, uint32_t count, int iters, i
         rp.g = h->g;
         launch_reproject(rp, c1 - c0, s);
         if (c1 > c0) ++h->acc_launches;
+        if (update_map && c1 > c0) {  // KILO.cc:231 — always, even when no update happened
+            const StepInit& in = hin[first];
+            map_insert_bucket(h->map, h->g, h->pts.as<float4>(), h->chunks.as<ChunkDesc>(), c0, c1 - c0, in.pt_begin,
+                              in.pt_end - in.pt_begin, h->sc.as<ScanConst>(), h->step.as<ScanStep>(), h->ins_pts.p,
+                              h->ins_root.as<int>(), h->ins_pend.as<int>(), h->ins_touched.as<uint32_t>(),
+                              h->ins_counters.as<uint32_t>(), h->ins_list.as<uint32_t>(), s);
+            h->acc_launches += 4;
+        }
     }
     LK_CUDA(h, cudaGetLastError());
+    if (update_map) {
+        std::string err;
+        int rc = h->map.sync_counters(s, err);  // also a sync: the caller observes a finished insert
+        if (rc) return fail(h, rc, err);
+        uint32_t ovf = 0;
+        LK_CUDA(h, cudaMemcpy(&ovf, h->map.counters + 2, 4, cudaMemcpyDeviceToHost));
+        if (ovf) return fail(h, LK_ERR_CAPACITY, "map pools exhausted during UpdateVoxelMap (raise lk_map_reserve)");
+    }
     return LK_OK;
 }
 

@@ -1,0 +1,230 @@
+// lk_insert.cu — device-side VoxelMapManager::UpdateVoxelMap (voxel_map.cc:336-361) for one
+// bucket: step 4 of KILO::predictUpdatePoint (KILO.cc:215-231).
+//
+// The reference inserts the bucket's points one after another; points only interact when they
+// fall into the same ROOT voxel (every octree node belongs to exactly one root). So:
+//   P1  per point: world point + covariance with the UPDATED state (KILO.cc:218-228), insert key
+//       (voxelKeyFloor), find-or-create the root (CAS on the open-addressed table), count the
+//       point on its root, first toucher registers the root;
+//   P2  per touched root: reserve a slice of the pending list;
+//   P3  per point: drop the point index into its root's slice;
+//   P4  one warp per touched root: order the slice by point index (= the reference's insertion
+//       order) and run UpdateOctoTree sequentially on it, with the warp-cooperative plane refit.
+#include "lk_kernels.h"
+#include "lk_mapdev.h"
+#include "lk_octree.cuh"
+
+namespace lk {
+
+namespace {
+
+struct InsertArgs {
+    MapDev md;
+    Globals g;
+    const float4* pts;
+    const ChunkDesc* chunks;
+    uint32_t chunk_first;
+    const ScanConst* sc;
+    const ScanStep* step;
+    DevPoint* ipts;      // [bucket points] DevPoint per point
+    int* iroot;          // [bucket points] root node per point (-1 = dropped)
+    uint32_t pt_base;    // absolute index of the first point covered by this launch's scratch
+    int* pend;           // [node_cap * 3] count | offset | fill
+    uint32_t* touched;   // [bucket points]
+    uint32_t* counters;  // [0] n_touched  [1] list bump
+    uint32_t* list;      // [2 * bucket points]  (second half = sort scratch)
+    uint32_t n_pts;
+};
+
+__device__ __forceinline__ int hash_find_or_create(MapDev& md, const Globals& g, int kx, int ky, int kz) {
+    uint32_t i = hash_key(kx, ky, kz) & md.hash_mask;
+    for (uint32_t probe = 0; probe <= md.hash_mask; ++probe) {
+        int* nodep = &md.slots[i].node;
+        int node = *(volatile int*)nodep;
+        if (node == -1) {
+            int old = atomicCAS(nodep, -1, -2);
+            if (old == -1) {
+                md.slots[i].kx = kx; md.slots[i].ky = ky; md.slots[i].kz = kz;
+                uint32_t nd = atomicAdd(md.n_nodes, 1u);
+                if (nd >= md.node_cap) {
+                    atomicOr(md.overflow, 1u);
+                    __threadfence();
+                    atomicExch(nodep, -3);  // poisoned slot: key present, no node
+                    return -1;
+                }
+                init_root_node(md, g, nd, kx, ky, kz);
+                atomicAdd(md.n_roots, 1u);
+                __threadfence();
+                atomicExch(nodep, (int)nd);
+                return (int)nd;
+            }
+            node = old;
+        }
+        while (node == -2) node = *(volatile int*)nodep;  // another thread is publishing this slot
+        __threadfence();
+        const int sx = *(volatile int*)&md.slots[i].kx, sy = *(volatile int*)&md.slots[i].ky, sz = *(volatile int*)&md.slots[i].kz;
+        if (sx == kx && sy == ky && sz == kz) return node >= 0 ? node : -1;
+        i = (i + 1) & md.hash_mask;
+    }
+    atomicOr(md.overflow, 4u);
+    return -1;
+}
+
+// P1 — also the re-projection's covariance half (KILO.cc:225-228).
+__global__ void __launch_bounds__(256) k_insert_p1(const __grid_constant__ InsertArgs a) {
+    __shared__ ScanConst s_sc;
+    const int tid = threadIdx.x;
+    const ChunkDesc cd = a.chunks[a.chunk_first + blockIdx.x];
+    if (tid < (int)(sizeof(ScanConst) / sizeof(double)))
+        reinterpret_cast<double*>(&s_sc)[tid] = reinterpret_cast<const double*>(a.sc + cd.scan)[tid];
+    __syncthreads();
+    const Globals& g = a.g;
+    MapDev md = a.md;
+    for (uint32_t i = tid; i < cd.count; i += blockDim.x) {
+        const float4 pt = __ldg(a.pts + cd.start + i);
+        const double bx = pt.x, by = pt.y, bz0 = pt.z;
+        const double pix = g.Re[0] * bx + g.Re[1] * by + g.Re[2] * bz0 + g.te[0];
+        const double piy = g.Re[3] * bx + g.Re[4] * by + g.Re[5] * bz0 + g.te[1];
+        const double piz = g.Re[6] * bx + g.Re[7] * by + g.Re[8] * bz0 + g.te[2];
+        const double* R = s_sc.R;
+        DevPoint p;
+        p.pw[0] = R[0] * pix + R[1] * piy + R[2] * piz + s_sc.p[0];
+        p.pw[1] = R[3] * pix + R[4] * piy + R[5] * piz + s_sc.p[1];
+        p.pw[2] = R[6] * pix + R[7] * piy + R[8] * piz + s_sc.p[2];
+        // body covariance (calcBodyCov saw pb.z == 0 -> 1e-4)
+        const double bz = (bz0 == 0.0) ? 0.0001 : bz0;
+        const double r2 = bx * bx + by * by + bz * bz;
+        const float range = (float)sqrt(r2);
+        const double range2 = (double)range * (double)range;
+        const double inv = 1.0 / sqrt(r2);
+        const double ux = bx * inv, uy = by * inv, uz = bz * inv;
+        // M = R Re ; mu = M u
+        double M[9];
+        mat3_mul(R, g.Re, M);
+        const double mu[3] = {M[0] * ux + M[1] * uy + M[2] * uz, M[3] * ux + M[4] * uy + M[5] * uz, M[6] * ux + M[7] * uy + M[8] * uz};
+        double MMt[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) MMt[r * 3 + c] = M[r * 3] * M[c * 3] + M[r * 3 + 1] * M[c * 3 + 1] + M[r * 3 + 2] * M[c * 3 + 2];
+        const double ca = (double)g.rv - range2 * g.dv, cb = range2 * g.dv;
+        // G = R [pi]x ; G P_tt G^T
+        const double K[9] = {0, -piz, piy, piz, 0, -pix, -piy, pix, 0};
+        double G[9], GP[9];
+        mat3_mul(R, K, G);
+        const double* S = s_sc.Pth;
+        const double Pt[9] = {S[0], S[1], S[2], S[1], S[3], S[4], S[2], S[4], S[5]};
+        mat3_mul(G, Pt, GP);
+        const double* Sp = s_sc.Ppp;
+        const double Pp[9] = {Sp[0], Sp[1], Sp[2], Sp[1], Sp[3], Sp[4], Sp[2], Sp[4], Sp[5]};
+        const int ut[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const int r = ut[q][0], c = ut[q][1];
+            p.var[q] = ca * mu[r] * mu[c] + cb * MMt[r * 3 + c] + (GP[r * 3] * G[c * 3] + GP[r * 3 + 1] * G[c * 3 + 1] + GP[r * 3 + 2] * G[c * 3 + 2]) +
+                       Pp[r * 3 + c];
+        }
+        p.pad = 0.0;
+        const uint32_t li = cd.start + i - a.pt_base;
+        a.ipts[li] = p;
+        // voxelKeyFloor(point_w, (double)(float)voxel_size)  (voxel_map.cc:337,343)
+        const double vs = (double)g.voxel_f;
+        const int kx = (int)floor(p.pw[0] / vs), ky = (int)floor(p.pw[1] / vs), kz = (int)floor(p.pw[2] / vs);
+        const int root = hash_find_or_create(md, g, kx, ky, kz);
+        a.iroot[li] = root;
+        if (root >= 0) {
+            const int c = atomicAdd(&a.pend[root * 3], 1);
+            if (c == 0) a.touched[atomicAdd(&a.counters[0], 1u)] = (uint32_t)root;
+        }
+    }
+}
+
+__global__ void k_insert_p2(const __grid_constant__ InsertArgs a) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.counters[0]) return;
+    const uint32_t root = a.touched[t];
+    const int cnt = a.pend[root * 3];
+    a.pend[root * 3 + 1] = (int)atomicAdd(&a.counters[1], (uint32_t)cnt);
+    a.pend[root * 3 + 2] = 0;
+}
+
+__global__ void k_insert_p3(const __grid_constant__ InsertArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_pts) return;
+    const int root = a.iroot[i];
+    if (root < 0) return;
+    const int slot = atomicAdd(&a.pend[root * 3 + 2], 1);
+    a.list[a.pend[root * 3 + 1] + slot] = i;
+}
+
+__global__ void __launch_bounds__(128) k_insert_p4(const __grid_constant__ InsertArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpTile* tiles = reinterpret_cast<WarpTile*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpTile* wt = tiles + warp;
+    if (lane == 0) {
+        mbar_init(&wt->bar, 1);
+        wt->phase = 0;
+        mbar_init_fence();
+    }
+    __syncwarp();
+    const uint32_t t = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (t >= a.counters[0]) return;
+    const uint32_t root = a.touched[t];
+    const int cnt = a.pend[root * 3];
+    const int off = a.pend[root * 3 + 1];
+    uint32_t* src = a.list + off;
+    uint32_t* dst = a.list + a.n_pts + off;
+    // rank sort by point index = the order UpdateVoxelMap walks input_points
+    for (int j = lane; j < cnt; j += 32) {
+        const uint32_t v = src[j];
+        int rank = 0;
+        for (int k = 0; k < cnt; ++k) rank += (src[k] < v) ? 1 : 0;
+        dst[rank] = v;
+    }
+    __syncwarp();
+    MapDev md = a.md;
+    for (int j = 0; j < cnt; ++j) {
+        const DevPoint p = a.ipts[dst[j]];
+        warp_update_octo_tree(md, a.g, wt, root, p, lane);
+    }
+    __syncwarp();
+    if (lane == 0) a.pend[root * 3] = 0;
+}
+
+}  // namespace
+
+// Scratch owned by the caller (lk_api): sized for the largest bucket.
+int map_insert_bucket(MapDevHost& mh, const Globals& g, const float4* pts, const ChunkDesc* chunks, uint32_t chunk_first,
+                      uint32_t n_chunks, uint32_t pt_begin, uint32_t n_pts, const ScanConst* sc, const ScanStep* step,
+                      void* ipts, int* iroot, int* pend, uint32_t* touched, uint32_t* counters, uint32_t* list,
+                      cudaStream_t s) {
+    if (!n_pts || !n_chunks) return LK_OK;
+    InsertArgs a;
+    a.md = mh.dev();
+    a.g = g;
+    a.pts = pts;
+    a.chunks = chunks;
+    a.chunk_first = chunk_first;
+    a.sc = sc;
+    a.step = step;
+    a.ipts = reinterpret_cast<DevPoint*>(ipts);
+    a.iroot = iroot;
+    a.pt_base = pt_begin;
+    a.pend = pend;
+    a.touched = touched;
+    a.counters = counters;
+    a.list = list;
+    a.n_pts = n_pts;
+    cudaMemsetAsync(counters, 0, 8, s);
+    k_insert_p1<<<n_chunks, 256, 0, s>>>(a);
+    k_insert_p2<<<(n_pts + 255) / 256, 256, 0, s>>>(a);
+    k_insert_p3<<<(n_pts + 255) / 256, 256, 0, s>>>(a);
+    const int wpb = 4;
+    k_insert_p4<<<(n_pts + wpb - 1) / wpb, wpb * 32, wpb * sizeof(WarpTile), s>>>(a);
+    return LK_OK;
+}
+
+size_t insert_point_bytes() { return sizeof(DevPoint); }
+
+}  // namespace lk

@@ -39,6 +39,12 @@ class MapDevHost {
 // lk_mapbuild.cu
 int map_build_device(MapDevHost& mh, const Globals& g, const float* d_xyz_world, const float* d_xyz_body, uint32_t n,
                      const double* rot, const double* rot_cov, const double* pos_cov, cudaStream_t s, std::string& err);
+// lk_insert.cu — UpdateVoxelMap for one bucket (scratch buffers owned by the caller)
+int map_insert_bucket(MapDevHost& mh, const Globals& g, const float4* pts, const ChunkDesc* chunks, uint32_t chunk_first,
+                      uint32_t n_chunks, uint32_t pt_begin, uint32_t n_pts, const ScanConst* sc, const ScanStep* step,
+                      void* ipts, int* iroot, int* pend, uint32_t* touched, uint32_t* counters, uint32_t* list,
+                      cudaStream_t s);
+size_t insert_point_bytes();
 // lk_mapio.cu
 int map_upload_blob(MapDevHost& mh, const Globals& g, const void* blob, size_t bytes, cudaStream_t s, std::string& err);
 int map_download_blob(MapDevHost& mh, void* blob, size_t capacity, size_t* bytes_out, cudaStream_t s, std::string& err);

@@ -63,3 +63,55 @@ def test_map_upload_download_roundtrip():
     eng.map_upload(blob)
     st = mapcmp.compare_blobs(blob, eng.map_download(), rtol=1e-15)
     assert st["planes"] == 576
+
+
+def _stream_case(streaming, iters=1, stream0=700, empty_map=False, n_scans=2):
+    import test_gpu_parity as tp
+    cfg, blob, scans = scenes.box_scene(batch=2, streaming=streaming, stream0=stream0)
+    x0 = tp._moving_state() if streaming else abi.default_states(1)
+    P0 = abi.init_cov(1)
+    clk = np.zeros(1, abi.CLOCK_DTYPE); clk["last_predict_time"] = 9.99; clk["last_update_time"] = 9.985
+    o = lko.Oracle(cfg)
+    eng = Engine(cfg)
+    if not empty_map:
+        o.map_import(blob)
+        eng.map_upload(blob)
+    o.set_filter(x0, P0, abi.process_cov_Q(cfg), clk)
+    o.set_options(gain_mode=lko.GAIN_INFORMATION, iters=iters, update_map=True)
+    xg, Pg, cg = x0.copy(), P0.copy(), clk.copy()
+    t0 = 10.0
+    for s in scans[:n_scans]:  # two consecutive scans of one stream: the second one sees the map the first one left
+        pts, offs, times = synth.bucketize(s, begin_time=t0)
+        ro = o.process_scan(t0, pts)
+        out = eng.scan_update(xg, Pg, abi.process_cov_Q(cfg), cg, pts, [0, len(pts)], times, scan_bucket_ptr=[0, len(times)],
+                              bucket_offsets=offs, iters=iters, update_map=True)
+        xo, Po, _, clko = o.get_filter()
+        assert int(out["n_eff"][0]) == ro["n_eff"]
+        assert scenes.rel_state_err(out["x"], xo, x0) < 1e-5
+        assert scenes.rel_cov_err(out["P"][0], Po) < 1e-5
+        xg, Pg, cg = out["x"], out["P"], out["clk"]
+        t0 += 0.1
+    # the device state differs from the oracle's by ~1e-11 relative, so do the inserted points
+    st = mapcmp.compare_blobs(o.map_export(), eng.map_download(), rtol=1e-5, pt_atol=1e-8, var_rtol=1e-6)
+    return st
+
+
+def test_update_map_scan_at_once():
+    """One bucket per scan: update, re-project, then UpdateVoxelMap of all ~28 k points (KILO.cc:215-231)."""
+    st = _stream_case(streaming=False)
+    assert st["planes"] > 3000
+
+
+@pytest.mark.parametrize("iters", [1, 2])
+def test_update_map_streaming(iters):
+    """~50 buckets per scan, map mutated between buckets (refits every 6th insertion per leaf, freezes
+    at 50 points, new roots / octants on demand) — the full reference loop on the device."""
+    st = _stream_case(streaming=True, iters=iters)
+    assert st["planes"] > 3000
+
+
+def test_update_map_from_empty():
+    """No prior map: the scan finds no residuals at first and only inserts (the map, roots included,
+    is created by UpdateVoxelMap); later buckets of the same scan already match against it."""
+    st = _stream_case(streaming=True, empty_map=True, stream0=900, n_scans=1)
+    assert st["nodes"] > 3000 and st["points"] > 20000
