@@ -137,3 +137,35 @@ def test_streaming_buckets_static_map(fused, iters):
     assert out["clk"]["last_update_time"][0] == clko["last_update_time"][0]
     np.testing.assert_allclose(out["world"][:, :3], ro["world"][:, :3], rtol=0, atol=5e-6)
     np.testing.assert_array_equal(out["world"][:, 3], ro["world"][:, 3])
+
+
+def test_golden_fixtures_on_gpu():
+    """The committed fixtures (tests/golden/, made by make_golden.py from the oracle in the build
+    container) replayed on the device: config 1, and one streaming scan with map updates."""
+    import os
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    g = np.load(os.path.join(gdir, "config1_planar.npz"))
+    cfg, blob, pts = scenes.planar_scene()
+    assert np.array_equal(pts, g["pts"])
+    x0 = abi.default_states(1); P0 = abi.init_cov(1)
+    eng = Engine(cfg); eng.map_upload(blob)
+    out = eng.scan_update(x0, P0, abi.process_cov_Q(cfg), np.zeros(1, abi.CLOCK_DTYPE), pts, [0, len(pts)], [0.0])
+    xg = g["x"].view(abi.STATE_DTYPE)
+    assert int(out["n_eff"][0]) == int(g["n_eff"])
+    assert scenes.rel_state_err(out["x"], xg, x0) < TOL and scenes.rel_cov_err(out["P"][0], g["P"]) < TOL
+
+    g = np.load(os.path.join(gdir, "streaming_box.npz"))
+    cfg, blob, scans = scenes.box_scene(batch=1, streaming=True, stream0=700, ground_half_extent=12.0)
+    pts, offs, times = synth.bucketize(scans[0], begin_time=10.0)
+    x0 = g["x0"].view(abi.STATE_DTYPE); P0 = abi.init_cov(1)
+    clk = np.zeros(1, abi.CLOCK_DTYPE); clk["last_predict_time"] = 9.99; clk["last_update_time"] = 9.985
+    eng = Engine(cfg); eng.map_upload(blob)
+    out = eng.scan_update(x0, P0, abi.process_cov_Q(cfg), clk, pts, [0, len(pts)], times, scan_bucket_ptr=[0, len(times)],
+                          bucket_offsets=offs, update_map=True)
+    assert int(out["n_eff"][0]) == int(g["n_eff"])
+    assert scenes.rel_state_err(out["x"], g["x"].view(abi.STATE_DTYPE), x0) < TOL
+    assert scenes.rel_cov_err(out["P"][0], g["P"]) < TOL
+    np.testing.assert_array_equal(out["clk"].view(np.float64), g["clk"])
+    st = eng.map_stats()
+    assert st["roots"] == int(g["n_roots"]) and st["nodes"] >= int(g["n_nodes"]) and st["points"] == int(g["n_points"])
+    assert st["planes"] == int(g["n_planes"])
