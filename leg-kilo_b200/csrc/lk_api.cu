@@ -490,7 +490,17 @@ int lk_timer_stop(lk_handle h, float* total_ms, float* residual_kernel_ms, uint3
 }
 
 // Enqueue the hot path for scans [first, first+count) of the staged batch; no host sync.
-int lk_batch_run_range(lk_handle h, uint32_t first, uint32_t count, int iters, int update_map) {
+namespace {
+struct MeasQueue {
+    const lk_imu_meas* d_imu = nullptr;
+    const lk_kinimu_meas* d_kin = nullptr;
+    const double* stamps = nullptr;  // host copy of the stamps
+    uint32_t n = 0;
+    double gravity = 9.81, acc_norm = 1.0;
+};
+}  // namespace
+
+static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters, int update_map, const MeasQueue* mq) {
     if (!h) return LK_ERR_INVALID_ARG;
     if (h->batch <= 0) return fail(h, LK_ERR_NOT_READY, "lk_batch_run before lk_batch_stage");
     if (iters < 1) return fail(h, LK_ERR_INVALID_ARG, "iters must be >= 1");
@@ -561,6 +571,14 @@ int lk_batch_run_range(lk_handle h, uint32_t first, uint32_t count, int iters, i
         fa.mv.slots = h->map.slots;
         fa.mv.hash_mask = (uint32_t)(h->map.hash_cap - 1);
         fa.mv.nodes = h->map.nodes;
+        if (mq) {
+            fa.imu = mq->d_imu;
+            fa.kin = mq->d_kin;
+            fa.n_meas = mq->n;
+            fa.gravity = mq->gravity;
+            fa.acc_norm = mq->acc_norm;
+        }
+        fa.ecfg = h->ec;
         fa.trace = h->trace_on ? h->trace.as<unsigned long long>() : nullptr;
         fa.g = h->g;
         if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
@@ -570,9 +588,27 @@ int lk_batch_run_range(lk_handle h, uint32_t first, uint32_t count, int iters, i
         ++h->acc_residual_launches;
         return LK_OK;
     }
+    uint32_t mi = 0;
+    if (mq) {  // the queue is applied BEFORE bucket 0 as well, so the filter is re-loaded here, not in the kernel
+        LK_CUDA(h, cudaMemcpyAsync(h->x.as<lk_state>() + first, h->x_in.as<lk_state>() + first, sizeof(lk_state), cudaMemcpyDeviceToDevice, s));
+        LK_CUDA(h, cudaMemcpyAsync(h->P.as<double>() + (size_t)first * 900, h->P_in.as<double>() + (size_t)first * 900, 900 * 8, cudaMemcpyDeviceToDevice, s));
+        LK_CUDA(h, cudaMemcpyAsync(h->clk.as<lk_stream_clock>() + first, h->clk_in.as<lk_stream_clock>() + first, sizeof(lk_stream_clock), cudaMemcpyDeviceToDevice, s));
+        LK_CUDA(h, cudaMemsetAsync(h->n_eff.as<uint32_t>() + first, 0, 4, s));
+    }
     for (uint32_t k = 0; k < h->n_steps; ++k) {
         const StepInit* hin = h->h_inits.data() + (size_t)k * batch;
         uint32_t c0 = hin[first].chunk_begin, c1 = hin[first + count - 1].chunk_end;
+        if (mq && hin[first].active) {  // samples with stamp < bucket time (KILO.cc:379-390)
+            uint32_t m1 = mi;
+            while (m1 < mq->n && mq->stamps[m1] < hin[first].t_bucket) ++m1;
+            if (m1 > mi) {
+                launch_filter_obs(h->x.as<double>() + (size_t)first * 36, h->P.as<double>() + (size_t)first * 900, h->Q.as<double>(),
+                                  h->clk.as<lk_stream_clock>() + first, mq->d_imu ? mq->d_imu + mi : nullptr,
+                                  mq->d_kin ? mq->d_kin + mi : nullptr, m1 - mi, h->ec, mq->gravity, mq->acc_norm, s);
+                ++h->acc_launches;
+                mi = m1;
+            }
+        }
         PredictArgs pa;
         pa.init = h->stepinit.as<StepInit>() + (size_t)k * batch;
         pa.step = h->step.as<ScanStep>();
@@ -586,7 +622,7 @@ int lk_batch_run_range(lk_handle h, uint32_t first, uint32_t count, int iters, i
         pa.x_in = h->x_in.as<double>();
         pa.P_in = h->P_in.as<double>();
         pa.clk_in = h->clk_in.as<lk_stream_clock>();
-        pa.reset = (k == 0) ? 1 : 0;
+        pa.reset = (k == 0 && !mq) ? 1 : 0;
         pa.scan_first = (int)first;
         pa.batch = (int)count;
         launch_predict_prepare(pa, s);
@@ -629,6 +665,10 @@ int lk_batch_run_range(lk_handle h, uint32_t first, uint32_t count, int iters, i
         if (ovf) return fail(h, LK_ERR_CAPACITY, "map pools exhausted during UpdateVoxelMap (raise lk_map_reserve)");
     }
     return LK_OK;
+}
+
+int lk_batch_run_range(lk_handle h, uint32_t first, uint32_t count, int iters, int update_map) {
+    return run_range_impl(h, first, count, iters, update_map, nullptr);
 }
 
 int lk_batch_run(lk_handle h, int iters, int update_map) {
@@ -759,20 +799,118 @@ int lk_predict(lk_handle h, int batch, lk_state* x_inout, double* P_inout, const
     return LK_OK;
 }
 
-int lk_update_by_points(lk_handle h, lk_state*, double*, uint32_t, const double*, const double*, const double*) {
-    return fail(h, LK_ERR_NOT_READY, "lk_update_by_points not available in this build");
+namespace {
+int filter_upload(lk_handle h, const lk_state* x, const double* P, const double* Q, const lk_stream_clock* clk) {
+    cudaStream_t s = h->stream;
+    LK_CUDA(h, h->x.ensure(sizeof(lk_state)));
+    LK_CUDA(h, h->P.ensure(900 * 8));
+    LK_CUDA(h, h->Q.ensure(900 * 8));
+    LK_CUDA(h, h->clk.ensure(sizeof(lk_stream_clock)));
+    LK_CUDA(h, cudaMemcpyAsync(h->x.p, x, sizeof(lk_state), cudaMemcpyHostToDevice, s));
+    LK_CUDA(h, cudaMemcpyAsync(h->P.p, P, 900 * 8, cudaMemcpyHostToDevice, s));
+    if (Q) LK_CUDA(h, cudaMemcpyAsync(h->Q.p, Q, 900 * 8, cudaMemcpyHostToDevice, s));
+    if (clk) LK_CUDA(h, cudaMemcpyAsync(h->clk.p, clk, sizeof(lk_stream_clock), cudaMemcpyHostToDevice, s));
+    h->batch = 0;  // the filter buffers of a staged batch were borrowed
+    return LK_OK;
 }
-int lk_obs_imu(lk_handle h, lk_state*, double*, const double*, lk_stream_clock*, const lk_imu_meas*, uint32_t, double, double) {
-    return fail(h, LK_ERR_NOT_READY, "lk_obs_imu not available in this build");
+int filter_download(lk_handle h, lk_state* x, double* P, lk_stream_clock* clk) {
+    cudaStream_t s = h->stream;
+    LK_CUDA(h, cudaGetLastError());
+    LK_CUDA(h, cudaMemcpyAsync(x, h->x.p, sizeof(lk_state), cudaMemcpyDeviceToHost, s));
+    LK_CUDA(h, cudaMemcpyAsync(P, h->P.p, 900 * 8, cudaMemcpyDeviceToHost, s));
+    if (clk) LK_CUDA(h, cudaMemcpyAsync(clk, h->clk.p, sizeof(lk_stream_clock), cudaMemcpyDeviceToHost, s));
+    LK_CUDA(h, cudaStreamSynchronize(s));
+    return LK_OK;
 }
-int lk_obs_kinimu(lk_handle h, lk_state*, double*, const double*, lk_stream_clock*, const lk_kinimu_meas*, uint32_t, double,
-                  double) {
-    return fail(h, LK_ERR_NOT_READY, "lk_obs_kinimu not available in this build");
+}  // namespace
+
+int lk_update_by_points(lk_handle h, lk_state* x_inout, double* P_inout, uint32_t n, const double* pt_h, const double* pt_z,
+                        const double* pt_R) {
+    if (!h || !x_inout || !P_inout || (n && (!pt_h || !pt_z || !pt_R))) return fail(h, LK_ERR_INVALID_ARG, "null argument");
+    cudaSetDevice(h->device);
+    if (n == 0) return LK_OK;  // KILO.cc:188: no residual, no update
+    int rc = filter_upload(h, x_inout, P_inout, nullptr, nullptr);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    LK_CUDA(h, h->dbg_h.ensure((size_t)n * 48));
+    LK_CUDA(h, h->dbg_z.ensure((size_t)n * 8));
+    LK_CUDA(h, h->dbg_R.ensure((size_t)n * 8));
+    LK_CUDA(h, cudaMemcpyAsync(h->dbg_h.p, pt_h, (size_t)n * 48, cudaMemcpyHostToDevice, s));
+    LK_CUDA(h, cudaMemcpyAsync(h->dbg_z.p, pt_z, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    LK_CUDA(h, cudaMemcpyAsync(h->dbg_R.p, pt_R, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    launch_update_by_points(h->x.as<double>(), h->P.as<double>(), n, h->dbg_h.as<double>(), h->dbg_z.as<double>(),
+                            h->dbg_R.as<double>(), s);
+    return filter_download(h, x_inout, P_inout, nullptr);
 }
-int lk_process_scan(lk_handle h, lk_state*, double*, const double*, lk_stream_clock*, const float*, uint32_t, const uint32_t*,
-                    const double*, uint32_t, const lk_imu_meas*, const lk_kinimu_meas*, uint32_t, double, double, int, int,
-                    float*, uint32_t*, uint32_t*) {
-    return fail(h, LK_ERR_NOT_READY, "lk_process_scan not available in this build");
+
+int lk_obs_imu(lk_handle h, lk_state* x_inout, double* P_inout, const double* Q, lk_stream_clock* clk_inout,
+               const lk_imu_meas* imu, uint32_t n, double gravity, double acc_norm) {
+    if (!h || !x_inout || !P_inout || !Q || !clk_inout || (n && !imu)) return fail(h, LK_ERR_INVALID_ARG, "null argument");
+    cudaSetDevice(h->device);
+    if (n == 0) return LK_OK;
+    int rc = filter_upload(h, x_inout, P_inout, Q, clk_inout);
+    if (rc) return rc;
+    LK_CUDA(h, h->tmp.ensure((size_t)n * sizeof(lk_imu_meas)));
+    LK_CUDA(h, cudaMemcpyAsync(h->tmp.p, imu, (size_t)n * sizeof(lk_imu_meas), cudaMemcpyHostToDevice, h->stream));
+    launch_filter_obs(h->x.as<double>(), h->P.as<double>(), h->Q.as<double>(), h->clk.as<lk_stream_clock>(),
+                      h->tmp.as<lk_imu_meas>(), nullptr, n, h->ec, gravity, acc_norm, h->stream);
+    return filter_download(h, x_inout, P_inout, clk_inout);
+}
+
+int lk_obs_kinimu(lk_handle h, lk_state* x_inout, double* P_inout, const double* Q, lk_stream_clock* clk_inout,
+                  const lk_kinimu_meas* kin, uint32_t n, double gravity, double acc_norm) {
+    if (!h || !x_inout || !P_inout || !Q || !clk_inout || (n && !kin)) return fail(h, LK_ERR_INVALID_ARG, "null argument");
+    cudaSetDevice(h->device);
+    if (n == 0) return LK_OK;
+    int rc = filter_upload(h, x_inout, P_inout, Q, clk_inout);
+    if (rc) return rc;
+    LK_CUDA(h, h->tmp.ensure((size_t)n * sizeof(lk_kinimu_meas)));
+    LK_CUDA(h, cudaMemcpyAsync(h->tmp.p, kin, (size_t)n * sizeof(lk_kinimu_meas), cudaMemcpyHostToDevice, h->stream));
+    launch_filter_obs(h->x.as<double>(), h->P.as<double>(), h->Q.as<double>(), h->clk.as<lk_stream_clock>(), nullptr,
+                      h->tmp.as<lk_kinimu_meas>(), n, h->ec, gravity, acc_norm, h->stream);
+    return filter_download(h, x_inout, P_inout, clk_inout);
+}
+
+int lk_process_scan(lk_handle h, lk_state* x_inout, double* P_inout, const double* Q, lk_stream_clock* clk_inout,
+                    const float* pts, uint32_t n_pts, const uint32_t* bucket_offsets, const double* bucket_times,
+                    uint32_t n_buckets, const lk_imu_meas* imu, const lk_kinimu_meas* kin, uint32_t n_meas, double gravity,
+                    double acc_norm, int iters, int update_map, float* pts_world_out, uint32_t* n_effective_out,
+                    uint32_t* n_consumed) {
+    if (!h || !x_inout || !P_inout || !Q || !clk_inout || !bucket_offsets || (n_buckets && !bucket_times))
+        return fail(h, LK_ERR_INVALID_ARG, "null argument");
+    if (imu && kin) return fail(h, LK_ERR_INVALID_ARG, "pass either imu or kin samples, not both (imu_mode_only_, KILO.cc:379)");
+    if (n_meas && !imu && !kin) return fail(h, LK_ERR_INVALID_ARG, "n_meas > 0 without samples");
+    uint32_t so[2] = {0, n_pts}, sb[2] = {0, n_buckets};
+    int rc = lk_batch_stage(h, 1, x_inout, P_inout, Q, clk_inout, pts, so, sb, bucket_offsets, bucket_times);
+    if (rc) return rc;
+    cudaSetDevice(h->device);
+    MeasQueue mq;
+    std::vector<double> stamps(n_meas);
+    if (n_meas) {
+        const size_t bytes = (size_t)n_meas * (imu ? sizeof(lk_imu_meas) : sizeof(lk_kinimu_meas));
+        LK_CUDA(h, h->tmp.ensure(bytes));
+        LK_CUDA(h, cudaMemcpyAsync(h->tmp.p, imu ? (const void*)imu : (const void*)kin, bytes, cudaMemcpyHostToDevice, h->stream));
+        for (uint32_t i = 0; i < n_meas; ++i) stamps[i] = imu ? imu[i].stamp : kin[i].stamp;
+        mq.d_imu = imu ? h->tmp.as<lk_imu_meas>() : nullptr;
+        mq.d_kin = kin ? h->tmp.as<lk_kinimu_meas>() : nullptr;
+        mq.stamps = stamps.data();
+        mq.n = n_meas;
+    }
+    mq.gravity = gravity;
+    mq.acc_norm = acc_norm;
+    rc = lk_timer_start(h);
+    if (rc) return rc;
+    rc = run_range_impl(h, 0, 1, iters, update_map, &mq);
+    if (rc) return rc;
+    rc = lk_timer_stop(h, nullptr, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    if (n_consumed) {  // samples older than the LAST bucket were applied; the rest stays queued at the caller
+        uint32_t c = 0;
+        if (n_buckets)
+            while (c < n_meas && stamps[c] < bucket_times[n_buckets - 1]) ++c;
+        *n_consumed = c;
+    }
+    return lk_batch_fetch(h, x_inout, P_inout, clk_inout, pts_world_out, n_effective_out);
 }
 
 }  // extern "C"

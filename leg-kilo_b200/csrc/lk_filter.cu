@@ -2,6 +2,7 @@
 // (eskf.cc:64-89, called as in KILO.cc:110-115) and the per-bucket preparation of the constants
 // the residual blocks read.
 #include "lk_kernels.h"
+#include "lk_obs.cuh"
 #include "lk_predict.cuh"
 
 namespace lk {
@@ -95,7 +96,106 @@ __global__ void __launch_bounds__(FB) k_predict_dt(double* x, double* P, const d
     }
 }
 
+struct ObsSmem {
+    BlockFilter f;
+    double clk[2];
+    double F[900], T[900], Ps[900];
+    ObsScratch obs;
+    double slice[(FB / 32) * 32];
+};
+
+// A queue of inertial (imu) or kinematic+inertial (kin) samples applied to ONE host-visible filter:
+// predictUpdateImu / predictUpdateKinImu per sample, in order (KILO.cc:235-314).
+__global__ void __launch_bounds__(FB) k_filter_obs(double* x, double* P, const double* Q, lk_stream_clock* clk,
+                                                   const lk_imu_meas* imu, const lk_kinimu_meas* kin, uint32_t n,
+                                                   lk_eskf_cfg cfg, double gravity, double acc_norm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ObsSmem* sm = reinterpret_cast<ObsSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 900; e += FB) sm->f.P[e] = P[e];
+    if (tid < 36) sm->f.x[tid] = x[tid];
+    if (tid < 2) sm->clk[tid] = reinterpret_cast<const double*>(clk)[tid];
+    __syncthreads();
+    for (uint32_t i = 0; i < n; ++i) {
+        const double t = imu ? imu[i].stamp : kin[i].stamp;
+        block_predict_to(&sm->f, sm->clk, t, sm->F, sm->T, sm->Ps, Q);
+        if (imu) block_obs_imu<FB>(&sm->f, &sm->obs, imu + i, &cfg, gravity, acc_norm);
+        else block_obs_kinimu<FB>(&sm->f, &sm->obs, kin + i, &cfg, gravity, acc_norm);
+        if (tid == 0) sm->clk[1] = t;  // last_state_update_time_ = current_time
+        __syncthreads();
+    }
+    for (int e = tid; e < 900; e += FB) P[e] = sm->f.P[e];
+    if (tid < 36) x[tid] = sm->f.x[tid];
+    if (tid < 2) reinterpret_cast<double*>(clk)[tid] = sm->clk[tid];
+}
+
+// ESKF::updateByPoints (eskf.cc:91-113) from explicit rows: information-form sums, then the block solve.
+__global__ void __launch_bounds__(FB) k_update_by_points(double* x, double* P, uint32_t n, const double* h,
+                                                         const double* z, const double* r) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ObsSmem* sm = reinterpret_cast<ObsSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < 900; e += FB) sm->f.P[e] = P[e];
+    if (tid < 36) sm->f.x[tid] = x[tid];
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+    for (uint32_t k = tid; k < n; k += FB) {
+        Row row;
+        for (int j = 0; j < 6; ++j) row.h[j] = h[(size_t)k * 6 + j];
+        row.z = z[k];
+        row.R = r[k];
+        const double w = 1.0 / row.R;
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const double hw = row.h[a] * w;
+#pragma unroll
+            for (int c = a; c < 6; ++c) acc[q++] += hw * row.h[c];
+            acc[ACC_B + a] += hw * row.z;
+        }
+        acc[ACC_SUMR] += row.R;
+        acc[ACC_CNT] += 1.0;
+    }
+    const double tot = warp_transpose_sum(acc, lane);
+    sm->slice[warp * 32 + lane] = tot;
+    __syncthreads();
+    if (tid < 32) {
+        double v = 0.0;
+        for (int w = 0; w < FB / 32; ++w) v += sm->slice[w * 32 + tid];
+        sm->f.acc[tid] = v;
+    }
+    __syncthreads();
+    block_solve_update<FB>(&sm->f, true);
+    __syncthreads();
+    for (int e = tid; e < 900; e += FB) P[e] = sm->f.P[e];
+    if (tid < 36) x[tid] = sm->f.x[tid];
+}
+
 }  // namespace
+
+void launch_filter_obs(double* x, double* P, const double* Q, lk_stream_clock* clk, const lk_imu_meas* imu,
+                       const lk_kinimu_meas* kin, uint32_t n, const lk_eskf_cfg& cfg, double gravity, double acc_norm,
+                       cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_filter_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ObsSmem));
+        cudaFuncSetAttribute(k_update_by_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ObsSmem));
+        attr = true;
+    }
+    k_filter_obs<<<1, FB, sizeof(ObsSmem), s>>>(x, P, Q, clk, imu, kin, n, cfg, gravity, acc_norm);
+}
+
+void launch_update_by_points(double* x, double* P, uint32_t n, const double* h, const double* z, const double* r,
+                             cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_filter_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ObsSmem));
+        cudaFuncSetAttribute(k_update_by_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ObsSmem));
+        attr = true;
+    }
+    k_update_by_points<<<1, FB, sizeof(ObsSmem), s>>>(x, P, n, h, z, r);
+}
 
 void launch_predict_prepare(const PredictArgs& a, cudaStream_t s) {
     if (a.batch <= 0) return;

@@ -8,6 +8,7 @@
 #include <cooperative_groups.h>
 
 #include "lk_kernels.h"
+#include "lk_obs.cuh"
 #include "lk_pass.cuh"
 #include "lk_predict.cuh"
 #include "lk_solve.cuh"
@@ -30,6 +31,7 @@ struct PredictScratch {
     double F[900];
     double T[900];
     double Ps[900];
+    ObsScratch obs;  // the IMU / Kin+IMU update follows its predict, so both live here
 };
 
 struct FusedSmem {
@@ -80,10 +82,28 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
     DebugRows dbg;
     dbg.ok = nullptr; dbg.h = nullptr; dbg.z = nullptr; dbg.R = nullptr; dbg.key = nullptr;
     int it_global = 0;
+    uint32_t mi = 0;  // next inertial / kinematic sample
 
     for (uint32_t k = 0; k < a.n_steps; ++k) {
         const StepInit in = a.inits[(size_t)k * a.batch + scan];
         if (!in.active) continue;
+        // 0) every queued inertial / kinematic sample older than this bucket (KILO.cc:379-390)
+        bool drained = false;
+        while (mi < a.n_meas) {
+            const double ts = a.imu ? a.imu[mi].stamp : a.kin[mi].stamp;
+            if (!(ts < in.t_bucket)) break;
+            block_predict_to(&sm->f, sm->clk, ts, sm->u.pr.F, sm->u.pr.T, sm->u.pr.Ps, a.Q);
+            if (a.imu) block_obs_imu<BLOCK>(&sm->f, &sm->u.pr.obs, a.imu + mi, &a.ecfg, a.gravity, a.acc_norm);
+            else block_obs_kinimu<BLOCK>(&sm->f, &sm->u.pr.obs, a.kin + mi, &a.ecfg, a.gravity, a.acc_norm);
+            if (tid == 0) sm->clk[1] = ts;
+            __syncthreads();
+            ++mi;
+            drained = true;
+        }
+        if (drained) {  // the scratch aliased the record tile
+            fence_proxy_async();
+            __syncthreads();
+        }
         // 1) predict (KILO.cc:110-115): covariance with dt since the last UPDATE, state with dt since
         //    the last PREDICT; F is built from the pre-propagation state.
         const double dtc = in.t_bucket - sm->clk[1];

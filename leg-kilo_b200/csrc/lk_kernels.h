@@ -80,6 +80,12 @@ struct ReprojectArgs {
 void launch_reproject(const ReprojectArgs& a, uint32_t n_chunks, cudaStream_t s);
 
 
+void launch_filter_obs(double* x, double* P, const double* Q, lk_stream_clock* clk, const lk_imu_meas* imu,
+                       const lk_kinimu_meas* kin, uint32_t n, const lk_eskf_cfg& cfg, double gravity, double acc_norm,
+                       cudaStream_t s);
+void launch_update_by_points(double* x, double* P, uint32_t n, const double* h, const double* z, const double* r,
+                             cudaStream_t s);
+
 // ---- fused per-scan persistent kernel (lk_fused.cu) -------------------------------------------
 struct FusedArgs {
     const float4* pts;
@@ -104,6 +110,11 @@ struct FusedArgs {
     int iters;
     int lane_cache;  // keep per-lane lookups / staged records across the iterations of a bucket
     MapView mv;
+    const lk_imu_meas* imu;      // queued samples interleaved with the buckets (exactly one of imu / kin, or none)
+    const lk_kinimu_meas* kin;
+    uint32_t n_meas;
+    double gravity, acc_norm;
+    lk_eskf_cfg ecfg;
     unsigned long long* trace;  // optional: 32 %globaltimer stamps per block
     Globals g;
 };

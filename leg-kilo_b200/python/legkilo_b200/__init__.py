@@ -248,6 +248,46 @@ class Engine:
         self._chk(lib().lk_debug_residuals(self.h, _p(x), _p(P), _p(pts), n, _p(ok), _p(h), _p(z), _p(R), _p(key)))
         return dict(ok=ok, h=h, z=z, R=R, key=key)
 
+    def update_by_points(self, x, P, h, z, R):
+        """ESKF::updateByPoints (eskf.cc:91-113) from explicit rows."""
+        x = np.array(x, abi.STATE_DTYPE, copy=True); P = np.array(P, np.float64, copy=True).reshape(900)
+        h = np.ascontiguousarray(h, np.float64).reshape(-1, 6); z = np.ascontiguousarray(z, np.float64)
+        R = np.ascontiguousarray(R, np.float64)
+        self._chk(lib().lk_update_by_points(self.h, _p(x), _p(P), len(z), _p(h), _p(z), _p(R)))
+        return x, P
+
+    def obs_imu(self, x, P, Q, clk, imu, gravity=9.81, acc_norm=1.0):
+        """KILO::predictUpdateImu per sample (KILO.cc:235-258)."""
+        x = np.array(x, abi.STATE_DTYPE, copy=True); P = np.array(P, np.float64, copy=True).reshape(900)
+        clk = np.array(clk, abi.CLOCK_DTYPE, copy=True); Q = np.ascontiguousarray(Q, np.float64)
+        imu = np.ascontiguousarray(imu, abi.IMU_DTYPE)
+        self._chk(lib().lk_obs_imu(self.h, _p(x), _p(P), _p(Q), _p(clk), _p(imu), len(imu), gravity, acc_norm))
+        return x, P, clk
+
+    def obs_kinimu(self, x, P, Q, clk, kin, gravity=9.81, acc_norm=1.0):
+        """KILO::predictUpdateKinImu per sample (KILO.cc:260-314)."""
+        x = np.array(x, abi.STATE_DTYPE, copy=True); P = np.array(P, np.float64, copy=True).reshape(900)
+        clk = np.array(clk, abi.CLOCK_DTYPE, copy=True); Q = np.ascontiguousarray(Q, np.float64)
+        kin = np.ascontiguousarray(kin, abi.KINIMU_DTYPE)
+        self._chk(lib().lk_obs_kinimu(self.h, _p(x), _p(P), _p(Q), _p(clk), _p(kin), len(kin), gravity, acc_norm))
+        return x, P, clk
+
+    def process_scan(self, x, P, Q, clk, pts, bucket_offsets, bucket_times, imu=None, kin=None, gravity=9.81, acc_norm=1.0,
+                     iters=1, update_map=True):
+        """The second lambda of KILO::process (KILO.cc:367-396) for one scan, inertial / kinematic queue
+        interleaved on the device."""
+        x = np.array(x, abi.STATE_DTYPE, copy=True); P = np.array(P, np.float64, copy=True).reshape(900)
+        clk = np.array(clk, abi.CLOCK_DTYPE, copy=True); Q = np.ascontiguousarray(Q, np.float64)
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 4)
+        bo = np.ascontiguousarray(bucket_offsets, np.uint32); bt = np.ascontiguousarray(bucket_times, np.float64)
+        imu = None if imu is None else np.ascontiguousarray(imu, abi.IMU_DTYPE)
+        kin = None if kin is None else np.ascontiguousarray(kin, abi.KINIMU_DTYPE)
+        nm = len(imu) if imu is not None else (len(kin) if kin is not None else 0)
+        world = np.zeros((len(pts), 4), np.float32); neff = np.zeros(1, np.uint32); ncons = np.zeros(1, np.uint32)
+        self._chk(lib().lk_process_scan(self.h, _p(x), _p(P), _p(Q), _p(clk), _p(pts), len(pts), _p(bo), _p(bt), len(bt), _p(imu),
+                                        _p(kin), nm, gravity, acc_norm, iters, int(update_map), _p(world), _p(neff), _p(ncons)))
+        return dict(x=x, P=P, clk=clk, world=world, n_eff=int(neff[0]), n_consumed=int(ncons[0]))
+
     def predict(self, x, P, Q, dt, prop_state=True, prop_cov=True):
         x = np.array(x, abi.STATE_DTYPE, copy=True); batch = len(x)
         P = np.array(P, np.float64, copy=True).reshape(batch, 900)

@@ -227,3 +227,36 @@ def bucketize(pts: np.ndarray, begin_time: float = 0.0):
     offs = np.concatenate([[0], brk, [len(s)]]).astype(np.uint32)
     times = begin_time + s[offs[:-1], 3].astype(np.float64)
     return s, offs, times
+
+
+# ---------------------------------------------------------------------------------------------
+# Inertial / kinematic sample streams
+# ---------------------------------------------------------------------------------------------
+
+def imu_stream(t0: float, t1: float, rate_hz: float = 400.0, stream: int = 41):
+    """lk_imu_meas samples on (t0, t1]: gravity-dominated accelerometer, small gyro, white noise."""
+    from . import abi
+    g = rng(stream)
+    n = int(np.floor((t1 - t0) * rate_hz))
+    m = np.zeros(n, abi.IMU_DTYPE)
+    m["stamp"] = t0 + (np.arange(n) + 1) / rate_hz
+    m["acc"] = np.array([0.15, -0.1, 9.79]) + 0.05 * g.standard_normal((n, 3))
+    m["gyr"] = np.array([0.01, -0.02, 0.12]) + 0.005 * g.standard_normal((n, 3))
+    return m
+
+
+def kinimu_stream(t0: float, t1: float, rate_hz: float = 400.0, stream: int = 43):
+    """lk_kinimu_meas samples (sensor_types.hpp:19-26): 2-4 feet in contact, trotting pattern."""
+    from . import abi
+    g = rng(stream)
+    im = imu_stream(t0, t1, rate_hz, stream)
+    n = len(im)
+    m = np.zeros(n, abi.KINIMU_DTYPE)
+    m["stamp"] = im["stamp"]; m["acc"] = im["acc"]; m["gyr"] = im["gyr"]
+    hip = np.array([[0.19, -0.13, -0.3], [0.19, 0.13, -0.3], [-0.19, -0.13, -0.3], [-0.19, 0.13, -0.3]])
+    m["foot_pos"] = hip[None] + 0.02 * g.standard_normal((n, 4, 3))
+    m["foot_vel"] = 0.05 * g.standard_normal((n, 4, 3))
+    phase = (np.arange(n) // 20) % 3
+    pat = np.array([[1, 0, 0, 1], [0, 1, 1, 0], [1, 1, 1, 1]], np.int32)
+    m["contact"] = pat[phase]
+    return m
