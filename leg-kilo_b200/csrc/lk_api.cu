@@ -133,13 +133,9 @@ void fill_globals(lk_context* c, const double* extR, const double* extT) {
 
 uint32_t chunk_size_for(uint32_t n) {
     // a function of the bucket alone, so results are bitwise independent of how a batch is
-    // sharded across GPUs (SURVEY §4 multi-GPU invariant). Small buckets: one point per thread
-    // (256-point chunks) for latency; large buckets: at most 512 chunks per bucket.
-    uint32_t c = (n + 511) / 512;
-    c = ((c + 255) / 256) * 256;
-    if (c < 256) c = 256;
-    if (c > 4096) c = 4096;
-    return c;
+    // sharded across GPUs (SURVEY §4 multi-GPU invariant). Buckets up to 64 Ki points: one point per
+    // thread (256-point chunks, latency first); larger ones: 2 048-point chunks streamed by warps.
+    return n <= 65536u ? 256u : 2048u;
 }
 
 cudaEvent_t kev_get(lk_context* c, size_t i) {

@@ -39,3 +39,11 @@ __device__ __forceinline__ void mbar_init_fence() {
 }
 
 }  // namespace lk
+
+namespace lk {
+// Ampere-style asynchronous 16-byte copy global -> shared (LDGSTS in SASS); completes per thread.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+}  // namespace lk

@@ -305,4 +305,126 @@ __device__ __forceinline__ void block_points_pass(PassSmem<NTHREADS>* ps, uint32
 #undef PT
 }
 
+
+// =================================================================================================
+// Throughput variant: every warp streams its own 32-point groups of the block's chunk with no
+// block-wide barrier inside the loop; records are staged by warp-cooperative 16-byte async copies
+// (two 256-byte records per warp instruction: 4 cache lines instead of 32); points that fail at
+// home only remember their neighbour key and are finished in bulk after the loop.
+// =================================================================================================
+template <int NTHREADS, int MAXPTS>
+struct StreamSmem {
+    __align__(16) unsigned char tile[NTHREADS * TILE_STRIDE];  // 32 slots per warp
+    struct Fallback {
+        uint32_t idx;
+        int nx, ny, nz;
+    } fb[MAXPTS];
+    uint32_t n_fb;
+    uint32_t pad[3];
+};
+
+__device__ __forceinline__ void prepare_point(float4 pt, const ScanConst& sc, const Globals& g, PointCtx& pc, float& lx,
+                                              float& ly, float& lz) {
+    const double bx = (double)pt.x, by = (double)pt.y, bz = (double)pt.z;
+    pc.pix = g.Re[0] * bx + g.Re[1] * by + g.Re[2] * bz + g.te[0];
+    pc.piy = g.Re[3] * bx + g.Re[4] * by + g.Re[5] * bz + g.te[1];
+    pc.piz = g.Re[6] * bx + g.Re[7] * by + g.Re[8] * bz + g.te[2];
+    pc.pbx = bx; pc.pby = by; pc.pbz = (bz == 0.0) ? 0.0001 : bz;  // calcBodyCov's mutation (voxel_map.cc:23)
+    pc.r2 = pc.pbx * pc.pbx + pc.pby * pc.pby + pc.pbz * pc.pbz;
+    const float range = (float)sqrt(pc.r2);
+    pc.range2 = (double)range * (double)range;
+    pc.pwx = sc.R[0] * pc.pix + sc.R[1] * pc.piy + sc.R[2] * pc.piz + sc.p[0];
+    pc.pwy = sc.R[3] * pc.pix + sc.R[4] * pc.piy + sc.R[5] * pc.piz + sc.p[1];
+    pc.pwz = sc.R[6] * pc.pix + sc.R[7] * pc.piy + sc.R[8] * pc.piz + sc.p[2];
+    if (g.voxel_pow2) {
+        lx = (float)(pc.pwx * g.inv_voxel); ly = (float)(pc.pwy * g.inv_voxel); lz = (float)(pc.pwz * g.inv_voxel);
+    } else {
+        lx = (float)(pc.pwx / g.voxel); ly = (float)(pc.pwy / g.voxel); lz = (float)(pc.pwz / g.voxel);
+    }
+    if (lx < 0) lx = (float)((double)lx - 1.0);
+    if (ly < 0) ly = (float)((double)ly - 1.0);
+    if (lz < 0) lz = (float)((double)lz - 1.0);
+}
+
+__device__ __forceinline__ bool eval_node(const MapView& mv, const PlaneRec& r, const PointCtx& pc, const ScanConst& sc,
+                                          const Globals& g, Row& row) {
+    double prob = 0.0;
+    if (r.flags & LK_NODE_IS_PLANE) return eval_plane(r, pc, sc, g, false, prob, row);
+    const uint32_t cmask = (r.flags >> LK_NODE_CHILDMASK_SHIFT) & 0xffu;
+    if (g.max_layer >= 1 && r.child_base >= 0 && cmask) return visit_subtree(mv.nodes, r.child_base, cmask, &pc, &sc, &g, &prob, &row);
+    return false;
+}
+
+template <int NTHREADS, int MAXPTS>
+__device__ __forceinline__ void block_points_stream(StreamSmem<NTHREADS, MAXPTS>* ss, const float4* __restrict__ pts,
+                                                    uint32_t count, const ScanConst& sc, const MapView& mv, const Globals& g,
+                                                    double (&acc)[32]) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NTHREADS / 32;
+    unsigned char* wtile = ss->tile + (size_t)warp * 32 * TILE_STRIDE;
+    const int half = lane >> 4, sub = lane & 15;
+    for (uint32_t g0 = warp * 32; g0 < count; g0 += NW * 32) {
+        const uint32_t i = g0 + lane;
+        const bool active = i < count;
+        PointCtx pc;
+        float lx = 0, ly = 0, lz = 0;
+        int kx = 0, ky = 0, kz = 0, root = -1;
+        if (active) {
+            prepare_point(__ldg(pts + i), sc, g, pc, lx, ly, lz);
+            kx = (int)lx; ky = (int)ly; kz = (int)lz;
+            const uint32_t ih = hash_key(kx, ky, kz) & mv.hash_mask;
+            root = resolve_pair(mv.slots, mv.hash_mask, ih, load_pair(mv.slots, ih), kx, ky, kz);
+        }
+        // cooperative gather: instruction j moves records of lanes 2j and 2j+1 (16 lanes x 16 B each)
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int r = __shfl_sync(0xffffffffu, root, 2 * j + half);
+            if (r >= 0) cp_async16(wtile + (size_t)(2 * j + half) * TILE_STRIDE + sub * 16,
+                                   reinterpret_cast<const unsigned char*>(mv.nodes + r) + sub * 16);
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        if (root >= 0) {
+            PlaneRec r;
+            plane_from_smem(wtile + (size_t)lane * TILE_STRIDE, r);
+            Row row;
+            if (eval_node(mv, r, pc, sc, g, row)) {
+                accumulate_row(row, acc);
+            } else {
+                // the ONE neighbour the reference falls back to (KILO.cc:156-178; voxel units vs metres)
+                const double q = (double)(g.voxel_f / 4.0f);
+                const double cx = (0.5 + kx) * (double)g.voxel_f, cy = (0.5 + ky) * (double)g.voxel_f, cz = (0.5 + kz) * (double)g.voxel_f;
+                int nx = kx, ny = ky, nz = kz;
+                if ((double)lx > cx + q) nx++; else if ((double)lx < cx - q) nx--;
+                if ((double)ly > cy + q) ny++; else if ((double)ly < cy - q) ny--;
+                if ((double)lz > cz + q) nz++; else if ((double)lz < cz - q) nz--;
+                if (nx != kx || ny != ky || nz != kz) {
+                    const uint32_t slot = atomicAdd(&ss->n_fb, 1u);
+                    ss->fb[slot].idx = i; ss->fb[slot].nx = nx; ss->fb[slot].ny = ny; ss->fb[slot].nz = nz;
+                }
+            }
+        }
+        __syncwarp();  // the tile is rewritten by the next group
+    }
+    __syncthreads();
+    const uint32_t n_fb = ss->n_fb;
+    for (uint32_t e = tid; e < n_fb; e += NTHREADS) {
+        const uint32_t i = ss->fb[e].idx;
+        const int nx = ss->fb[e].nx, ny = ss->fb[e].ny, nz = ss->fb[e].nz;
+        const uint32_t in = hash_key(nx, ny, nz) & mv.hash_mask;
+        const int near = resolve_pair(mv.slots, mv.hash_mask, in, load_pair(mv.slots, in), nx, ny, nz);
+        if (near < 0) continue;
+        PointCtx pc;
+        float lx, ly, lz;
+        prepare_point(__ldg(pts + i), sc, g, pc, lx, ly, lz);
+        PlaneRec r;
+        load_plane(mv.nodes + near, r);
+        Row row;
+        if (eval_node(mv, r, pc, sc, g, row)) accumulate_row(row, acc);
+    }
+    __syncthreads();
+    if (tid == 0) ss->n_fb = 0;
+}
+
 }  // namespace lk

@@ -133,6 +133,61 @@ __global__ void __launch_bounds__(BLOCK, (DEBUG || SINGLE) ? 1 : 2) k_residual(c
     }
 }
 
+constexpr int STREAM_MAXPTS = 2048;  // largest chunk lk_api.cu hands out
+
+union StreamUnion {  // the tail runs after the streaming loop: same storage
+    StreamSmem<BLOCK, STREAM_MAXPTS> stream;
+    TailSmem tail;
+};
+
+// Throughput variant for large batches: warps stream their 32-point groups independently, records
+// are staged by cooperative async copies, fallback points are finished in bulk, 2 CTAs per SM.
+__global__ void __launch_bounds__(BLOCK, 2) k_residual_stream(const __grid_constant__ ResidualArgs a) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ ScanConst s_sc;
+    __shared__ uint32_t s_last;
+    StreamUnion* su = reinterpret_cast<StreamUnion*>(s_raw);
+    TailSmem* ts = &su->tail;
+    const int tid = threadIdx.x;
+    const ChunkDesc cd = a.chunks[a.chunk_first + blockIdx.x];
+    if (tid < (int)(sizeof(ScanConst) / sizeof(double)))
+        reinterpret_cast<double*>(&s_sc)[tid] = reinterpret_cast<const double*>(a.sc + cd.scan)[tid];
+    if (tid == 0) su->stream.n_fb = 0;
+    __syncthreads();
+    MapView mv;
+    mv.slots = a.slots; mv.hash_mask = a.hash_mask; mv.nodes = a.nodes;
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+    block_points_stream<BLOCK, STREAM_MAXPTS>(&su->stream, a.pts + cd.start, cd.count, s_sc, mv, a.g, acc);
+
+    const int lane = tid & 31, warp = tid >> 5;
+    double* s_red = ts->slice;
+    double tot = warp_transpose_sum(acc, lane);
+    __syncthreads();
+    s_red[warp * 32 + lane] = tot;
+    __syncthreads();
+    if (tid < 32) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) v += s_red[w * 32 + tid];
+        a.partial[(size_t)(a.chunk_first + blockIdx.x) * PARTIAL_STRIDE + tid] = v;
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const ScanStep* sp = a.step + cd.scan;
+        uint32_t n_chunks = sp->chunk_end - sp->chunk_begin;
+        uint32_t t = atomicAdd(a.ticket + cd.scan, 1u);
+        s_last = (t == n_chunks - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        scan_solve(a, cd.scan, ts);
+    }
+}
+
 }  // namespace
 
 void launch_residual(const ResidualArgs& a, uint32_t n_chunks, bool debug, bool single, cudaStream_t s) {
@@ -150,8 +205,15 @@ void launch_residual(const ResidualArgs& a, uint32_t n_chunks, bool debug, bool 
         k_residual<true, false><<<n_chunks, BLOCK, smem, s>>>(a);
     else if (single)
         k_residual<false, true><<<n_chunks, BLOCK, smem, s>>>(a);
-    else
-        k_residual<false, false><<<n_chunks, BLOCK, smem, s>>>(a);
+    else {
+        static bool attr2 = false;
+        if (!attr2) {
+            cudaFuncSetAttribute(k_residual_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamUnion));
+            cudaFuncSetAttribute(k_residual_stream, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            attr2 = true;
+        }
+        k_residual_stream<<<n_chunks, BLOCK, sizeof(StreamUnion), s>>>(a);
+    }
 }
 
 // ---- re-projection with the updated state (KILO.cc:216-224) ---------------------------------
