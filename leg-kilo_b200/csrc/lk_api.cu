@@ -42,6 +42,26 @@ struct DevBuf {
     T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+struct DevView {  // a typed window into somebody else's device allocation
+    void* p = nullptr;
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaHostAlloc(&p, bytes + bytes / 4 + 4096, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = bytes + bytes / 4 + 4096;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 }  // namespace
 
 struct lk_context {
@@ -61,7 +81,12 @@ struct lk_context {
     uint64_t total_pts = 0;
     uint32_t total_chunks = 0, n_steps = 0, max_chunk_pts = 0;
     std::vector<uint32_t> step_chunk_ptr;
-    DevBuf pts, world, chunks, stepinit, x_in, P_in, clk_in, Q, x, P, clk, sc, step, partial, ticket, n_eff;
+    DevBuf pts, world, sc, step, partial, ticket;
+    // small per-call inputs / outputs travel as ONE packed copy each way (pinned staging blocks)
+    DevBuf small_in, small_out, fx, fP, fQ, fclk;
+    PinnedBuf h_small_in, h_small_out;
+    DevView chunks, stepinit, x_in, P_in, clk_in, Q, x, P, clk, n_eff;
+    size_t out_off_P = 0, out_off_clk = 0, out_off_neff = 0, out_bytes = 0;
     DevBuf dbg_ok, dbg_h, dbg_z, dbg_R, dbg_key, tmp, trace, bar;
     DevBuf ins_pts, ins_root, ins_pend, ins_touched, ins_counters, ins_list;
     uint64_t ins_pend_nodes = 0;
@@ -215,11 +240,12 @@ int lk_destroy(lk_handle h) {
     cudaStreamSynchronize(h->stream);
     h->map.release();
     DevBuf* bufs[] = {&h->pts, &h->world,
-                      &h->chunks, &h->stepinit, &h->x_in, &h->P_in, &h->clk_in, &h->Q, &h->x, &h->P, &h->clk, &h->sc,
-                      &h->step, &h->partial, &h->ticket, &h->n_eff, &h->dbg_ok, &h->dbg_h, &h->dbg_z, &h->dbg_R,
+                      &h->sc, &h->step, &h->partial, &h->ticket, &h->small_in, &h->small_out, &h->fx, &h->fP, &h->fQ, &h->fclk, &h->dbg_ok, &h->dbg_h, &h->dbg_z, &h->dbg_R,
                       &h->dbg_key, &h->tmp, &h->trace, &h->bar, &h->ins_pts, &h->ins_root, &h->ins_pend, &h->ins_touched,
                       &h->ins_counters, &h->ins_list};
     for (DevBuf* b : bufs) b->release();
+    h->h_small_in.release();
+    h->h_small_out.release();
     for (cudaEvent_t e : h->kev) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -357,9 +383,10 @@ int lk_map_build(lk_handle h, const float* xyz_world, const float* xyz_body, siz
 
 // ---- batch staging / run / fetch ----------------------------------------------------------------
 
-int lk_batch_stage(lk_handle h, int batch, const lk_state* x, const double* P, const double* Q,
-                   const lk_stream_clock* clk, const float* pts, const uint32_t* scan_offsets,
-                   const uint32_t* scan_bucket_ptr, const uint32_t* bucket_offsets, const double* bucket_times) {
+static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P, const double* Q,
+                      const lk_stream_clock* clk, const float* pts, const uint32_t* scan_offsets,
+                      const uint32_t* scan_bucket_ptr, const uint32_t* bucket_offsets, const double* bucket_times,
+                      bool sync_after) {
     if (!h) return LK_ERR_INVALID_ARG;
     if (batch <= 0 || !x || !P || !Q || !clk || !scan_offsets || !scan_bucket_ptr || !bucket_offsets || !bucket_times)
         return fail(h, LK_ERR_INVALID_ARG, "null / empty batch argument");
@@ -421,15 +448,6 @@ int lk_batch_stage(lk_handle h, int batch, const lk_state* x, const double* P, c
 
     LK_CUDA(h, h->pts.ensure(std::max<size_t>(total, 1) * 16));
     LK_CUDA(h, h->world.ensure(std::max<size_t>(total, 1) * 16));
-    LK_CUDA(h, h->chunks.ensure(std::max<size_t>(chunks.size(), 1) * sizeof(ChunkDesc)));
-    LK_CUDA(h, h->stepinit.ensure(std::max<size_t>(inits.size(), 1) * sizeof(StepInit)));
-    LK_CUDA(h, h->x_in.ensure((size_t)batch * sizeof(lk_state)));
-    LK_CUDA(h, h->P_in.ensure((size_t)batch * 900 * 8));
-    LK_CUDA(h, h->clk_in.ensure((size_t)batch * sizeof(lk_stream_clock)));
-    LK_CUDA(h, h->Q.ensure(900 * 8));
-    LK_CUDA(h, h->x.ensure((size_t)batch * sizeof(lk_state)));
-    LK_CUDA(h, h->P.ensure((size_t)batch * 900 * 8));
-    LK_CUDA(h, h->clk.ensure((size_t)batch * sizeof(lk_stream_clock)));
     LK_CUDA(h, h->sc.ensure((size_t)batch * sizeof(ScanConst)));
     LK_CUDA(h, h->step.ensure((size_t)batch * sizeof(ScanStep)));
     LK_CUDA(h, h->partial.ensure(2 * std::max<size_t>(chunks.size(), 1) * PARTIAL_STRIDE * 8));
@@ -438,17 +456,48 @@ int lk_batch_stage(lk_handle h, int batch, const lk_state* x, const double* P, c
         LK_CUDA(h, cudaMemsetAsync(h->bar.p, 0, 64, h->stream));
     }
     LK_CUDA(h, h->ticket.ensure((size_t)batch * 4));
-    LK_CUDA(h, h->n_eff.ensure((size_t)batch * 4));
+    // ---- small inputs: one pinned block, one H2D copy ------------------------------------------
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_chunks = 0;
+    const size_t o_inits = o_chunks + al(std::max<size_t>(chunks.size(), 1) * sizeof(ChunkDesc));
+    const size_t o_x = o_inits + al(std::max<size_t>(inits.size(), 1) * sizeof(StepInit));
+    const size_t o_P = o_x + al((size_t)batch * sizeof(lk_state));
+    const size_t o_clk = o_P + al((size_t)batch * 900 * 8);
+    const size_t o_Q = o_clk + al((size_t)batch * sizeof(lk_stream_clock));
+    const size_t in_bytes = o_Q + al(900 * 8);
+    LK_CUDA(h, h->small_in.ensure(in_bytes));
+    LK_CUDA(h, h->h_small_in.ensure(in_bytes));
+    char* hs = (char*)h->h_small_in.p;
+    if (!chunks.empty()) std::memcpy(hs + o_chunks, chunks.data(), chunks.size() * sizeof(ChunkDesc));
+    if (!inits.empty()) std::memcpy(hs + o_inits, inits.data(), inits.size() * sizeof(StepInit));
+    std::memcpy(hs + o_x, x, (size_t)batch * sizeof(lk_state));
+    std::memcpy(hs + o_P, P, (size_t)batch * 900 * 8);
+    std::memcpy(hs + o_clk, clk, (size_t)batch * sizeof(lk_stream_clock));
+    std::memcpy(hs + o_Q, Q, 900 * 8);
+    char* ds = (char*)h->small_in.p;
+    h->chunks.p = ds + o_chunks; h->stepinit.p = ds + o_inits; h->x_in.p = ds + o_x; h->P_in.p = ds + o_P;
+    h->clk_in.p = ds + o_clk; h->Q.p = ds + o_Q;
+    // ---- small outputs: one device block, fetched with one D2H copy ------------------------------
+    h->out_off_P = al((size_t)batch * sizeof(lk_state));
+    h->out_off_clk = h->out_off_P + al((size_t)batch * 900 * 8);
+    h->out_off_neff = h->out_off_clk + al((size_t)batch * sizeof(lk_stream_clock));
+    h->out_bytes = h->out_off_neff + al((size_t)batch * 4);
+    LK_CUDA(h, h->small_out.ensure(h->out_bytes));
+    LK_CUDA(h, h->h_small_out.ensure(h->out_bytes));
+    char* dout = (char*)h->small_out.p;
+    h->x.p = dout; h->P.p = dout + h->out_off_P; h->clk.p = dout + h->out_off_clk; h->n_eff.p = dout + h->out_off_neff;
     cudaStream_t s = h->stream;
     if (total) LK_CUDA(h, cudaMemcpyAsync(h->pts.p, pts, total * 16, cudaMemcpyHostToDevice, s));
-    if (!chunks.empty()) LK_CUDA(h, cudaMemcpyAsync(h->chunks.p, chunks.data(), chunks.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice, s));
-    if (!inits.empty()) LK_CUDA(h, cudaMemcpyAsync(h->stepinit.p, inits.data(), inits.size() * sizeof(StepInit), cudaMemcpyHostToDevice, s));
-    LK_CUDA(h, cudaMemcpyAsync(h->x_in.p, x, (size_t)batch * sizeof(lk_state), cudaMemcpyHostToDevice, s));
-    LK_CUDA(h, cudaMemcpyAsync(h->P_in.p, P, (size_t)batch * 900 * 8, cudaMemcpyHostToDevice, s));
-    LK_CUDA(h, cudaMemcpyAsync(h->clk_in.p, clk, (size_t)batch * sizeof(lk_stream_clock), cudaMemcpyHostToDevice, s));
-    LK_CUDA(h, cudaMemcpyAsync(h->Q.p, Q, 900 * 8, cudaMemcpyHostToDevice, s));
+    LK_CUDA(h, cudaMemcpyAsync(h->small_in.p, h->h_small_in.p, in_bytes, cudaMemcpyHostToDevice, s));
+    if (!sync_after) return LK_OK;
     LK_CUDA(h, cudaStreamSynchronize(s));  // the host tables above go out of scope
     return LK_OK;
+}
+
+int lk_batch_stage(lk_handle h, int batch, const lk_state* x, const double* P, const double* Q,
+                   const lk_stream_clock* clk, const float* pts, const uint32_t* scan_offsets,
+                   const uint32_t* scan_bucket_ptr, const uint32_t* bucket_offsets, const double* bucket_times) {
+    return stage_impl(h, batch, x, P, Q, clk, pts, scan_offsets, scan_bucket_ptr, bucket_offsets, bucket_times, true);
 }
 
 int lk_timer_start(lk_handle h) {
@@ -684,13 +733,17 @@ int lk_batch_fetch(lk_handle h, lk_state* x_out, double* P_out, lk_stream_clock*
     cudaSetDevice(h->device);
     cudaStream_t s = h->stream;
     const int batch = h->batch;
-    if (x_out) LK_CUDA(h, cudaMemcpyAsync(x_out, h->x.p, (size_t)batch * sizeof(lk_state), cudaMemcpyDeviceToHost, s));
-    if (P_out) LK_CUDA(h, cudaMemcpyAsync(P_out, h->P.p, (size_t)batch * 900 * 8, cudaMemcpyDeviceToHost, s));
-    if (clk_out) LK_CUDA(h, cudaMemcpyAsync(clk_out, h->clk.p, (size_t)batch * sizeof(lk_stream_clock), cudaMemcpyDeviceToHost, s));
+    const bool small = x_out || P_out || clk_out || n_effective_out;
+    if (small) LK_CUDA(h, cudaMemcpyAsync(h->h_small_out.p, h->small_out.p, h->out_bytes, cudaMemcpyDeviceToHost, s));
     if (pts_world_out && h->total_pts)
         LK_CUDA(h, cudaMemcpyAsync(pts_world_out, h->world.p, h->total_pts * 16, cudaMemcpyDeviceToHost, s));
-    if (n_effective_out) LK_CUDA(h, cudaMemcpyAsync(n_effective_out, h->n_eff.p, (size_t)batch * 4, cudaMemcpyDeviceToHost, s));
     LK_CUDA(h, cudaStreamSynchronize(s));
+    LK_CUDA(h, cudaGetLastError());
+    const char* ho = (const char*)h->h_small_out.p;
+    if (x_out) std::memcpy(x_out, ho, (size_t)batch * sizeof(lk_state));
+    if (P_out) std::memcpy(P_out, ho + h->out_off_P, (size_t)batch * 900 * 8);
+    if (clk_out) std::memcpy(clk_out, ho + h->out_off_clk, (size_t)batch * sizeof(lk_stream_clock));
+    if (n_effective_out) std::memcpy(n_effective_out, ho + h->out_off_neff, (size_t)batch * 4);
     return LK_OK;
 }
 
@@ -708,10 +761,15 @@ int lk_scan_update(lk_handle h, int batch, lk_state* x_inout, double* P_inout, c
                    lk_stream_clock* clk_inout, const float* pts, const uint32_t* scan_offsets,
                    const uint32_t* scan_bucket_ptr, const uint32_t* bucket_offsets, const double* bucket_times, int iters,
                    int update_map, float* pts_world_out, uint32_t* n_effective_out) {
-    int rc = lk_batch_stage(h, batch, x_inout, P_inout, Q, clk_inout, pts, scan_offsets, scan_bucket_ptr, bucket_offsets,
-                            bucket_times);
+    // one packed H2D (+ the points), the kernels, one packed D2H (+ the world cloud), ONE host sync
+    int rc = stage_impl(h, batch, x_inout, P_inout, Q, clk_inout, pts, scan_offsets, scan_bucket_ptr, bucket_offsets,
+                        bucket_times, false);
     if (rc) return rc;
-    rc = lk_batch_run(h, iters, update_map);
+    const int kt = h->kernel_timing;
+    h->kernel_timing = 0;
+    h->nev = 0;
+    rc = run_range_impl(h, 0, (uint32_t)batch, iters, update_map, nullptr);
+    h->kernel_timing = kt;
     if (rc) return rc;
     return lk_batch_fetch(h, x_inout, P_inout, clk_inout, pts_world_out, n_effective_out);
 }
@@ -778,10 +836,12 @@ int lk_predict(lk_handle h, int batch, lk_state* x_inout, double* P_inout, const
     if (!h || batch <= 0 || !x_inout || !P_inout || !Q || !dt) return fail(h, LK_ERR_INVALID_ARG, "null argument");
     cudaSetDevice(h->device);
     cudaStream_t s = h->stream;
-    LK_CUDA(h, h->x.ensure((size_t)batch * sizeof(lk_state)));
-    LK_CUDA(h, h->P.ensure((size_t)batch * 900 * 8));
-    LK_CUDA(h, h->Q.ensure(900 * 8));
+    LK_CUDA(h, h->fx.ensure((size_t)batch * sizeof(lk_state)));
+    LK_CUDA(h, h->fP.ensure((size_t)batch * 900 * 8));
+    LK_CUDA(h, h->fQ.ensure(900 * 8));
     LK_CUDA(h, h->tmp.ensure((size_t)batch * 8));
+    h->x.p = h->fx.p; h->P.p = h->fP.p; h->Q.p = h->fQ.p;
+    h->batch = 0;  // the views of a staged batch were re-pointed
     LK_CUDA(h, cudaMemcpyAsync(h->x.p, x_inout, (size_t)batch * sizeof(lk_state), cudaMemcpyHostToDevice, s));
     LK_CUDA(h, cudaMemcpyAsync(h->P.p, P_inout, (size_t)batch * 900 * 8, cudaMemcpyHostToDevice, s));
     LK_CUDA(h, cudaMemcpyAsync(h->Q.p, Q, 900 * 8, cudaMemcpyHostToDevice, s));
@@ -798,10 +858,11 @@ int lk_predict(lk_handle h, int batch, lk_state* x_inout, double* P_inout, const
 namespace {
 int filter_upload(lk_handle h, const lk_state* x, const double* P, const double* Q, const lk_stream_clock* clk) {
     cudaStream_t s = h->stream;
-    LK_CUDA(h, h->x.ensure(sizeof(lk_state)));
-    LK_CUDA(h, h->P.ensure(900 * 8));
-    LK_CUDA(h, h->Q.ensure(900 * 8));
-    LK_CUDA(h, h->clk.ensure(sizeof(lk_stream_clock)));
+    LK_CUDA(h, h->fx.ensure(sizeof(lk_state)));
+    LK_CUDA(h, h->fP.ensure(900 * 8));
+    LK_CUDA(h, h->fQ.ensure(900 * 8));
+    LK_CUDA(h, h->fclk.ensure(sizeof(lk_stream_clock)));
+    h->x.p = h->fx.p; h->P.p = h->fP.p; h->Q.p = h->fQ.p; h->clk.p = h->fclk.p;
     LK_CUDA(h, cudaMemcpyAsync(h->x.p, x, sizeof(lk_state), cudaMemcpyHostToDevice, s));
     LK_CUDA(h, cudaMemcpyAsync(h->P.p, P, 900 * 8, cudaMemcpyHostToDevice, s));
     if (Q) LK_CUDA(h, cudaMemcpyAsync(h->Q.p, Q, 900 * 8, cudaMemcpyHostToDevice, s));
@@ -877,7 +938,7 @@ int lk_process_scan(lk_handle h, lk_state* x_inout, double* P_inout, const doubl
     if (imu && kin) return fail(h, LK_ERR_INVALID_ARG, "pass either imu or kin samples, not both (imu_mode_only_, KILO.cc:379)");
     if (n_meas && !imu && !kin) return fail(h, LK_ERR_INVALID_ARG, "n_meas > 0 without samples");
     uint32_t so[2] = {0, n_pts}, sb[2] = {0, n_buckets};
-    int rc = lk_batch_stage(h, 1, x_inout, P_inout, Q, clk_inout, pts, so, sb, bucket_offsets, bucket_times);
+    int rc = stage_impl(h, 1, x_inout, P_inout, Q, clk_inout, pts, so, sb, bucket_offsets, bucket_times, false);
     if (rc) return rc;
     cudaSetDevice(h->device);
     MeasQueue mq;
@@ -894,11 +955,11 @@ int lk_process_scan(lk_handle h, lk_state* x_inout, double* P_inout, const doubl
     }
     mq.gravity = gravity;
     mq.acc_norm = acc_norm;
-    rc = lk_timer_start(h);
-    if (rc) return rc;
+    const int kt = h->kernel_timing;
+    h->kernel_timing = 0;
+    h->nev = 0;
     rc = run_range_impl(h, 0, 1, iters, update_map, &mq);
-    if (rc) return rc;
-    rc = lk_timer_stop(h, nullptr, nullptr, nullptr, nullptr);
+    h->kernel_timing = kt;
     if (rc) return rc;
     if (n_consumed) {  // samples older than the LAST bucket were applied; the rest stays queued at the caller
         uint32_t c = 0;

@@ -363,14 +363,18 @@ __device__ __forceinline__ void block_points_stream(StreamSmem<NTHREADS, MAXPTS>
     constexpr int NW = NTHREADS / 32;
     unsigned char* wtile = ss->tile + (size_t)warp * 32 * TILE_STRIDE;
     const int half = lane >> 4, sub = lane & 15;
+    float4 pt_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp * 32 + lane < count) pt_next = __ldg(pts + warp * 32 + lane);
     for (uint32_t g0 = warp * 32; g0 < count; g0 += NW * 32) {
         const uint32_t i = g0 + lane;
         const bool active = i < count;
+        const float4 pt = pt_next;
+        if (i + NW * 32 < count) pt_next = __ldg(pts + i + NW * 32);  // next group's point: off the critical path
         PointCtx pc;
         float lx = 0, ly = 0, lz = 0;
         int kx = 0, ky = 0, kz = 0, root = -1;
         if (active) {
-            prepare_point(__ldg(pts + i), sc, g, pc, lx, ly, lz);
+            prepare_point(pt, sc, g, pc, lx, ly, lz);
             kx = (int)lx; ky = (int)ly; kz = (int)lz;
             const uint32_t ih = hash_key(kx, ky, kz) & mv.hash_mask;
             root = resolve_pair(mv.slots, mv.hash_mask, ih, load_pair(mv.slots, ih), kx, ky, kz);
