@@ -43,6 +43,15 @@ WORKLOADS = {
 }
 
 
+def ncu_traffic(kernel):
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(kernel)
+    except (OSError, ValueError):
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -151,13 +160,88 @@ def cpu_reference_run(wl, w, scan_ids, nthreads, gain_information=True):
     return sec, xo, Po, ne, int(offs[-1])
 
 
+def stream_latency(args):
+    """BASELINE configs[4]: 10 Hz stream of scans, ~50 time buckets each, inertial (nclt: only_imu_use) or
+    kinematic+inertial (leg_fusion) queue interleaved, map updated after every bucket. One STEP = one scan
+    through lk_process_scan with HOST buffers (this mode is end-to-end by nature). Reports p50 per-scan ms."""
+    from legkilo_b200 import Engine
+    cfgname = "nclt" if args.workload == "nclt_stream" else "leg_fusion"
+    cfg = abi.CONFIGS[cfgname]
+    R, t = abi.extrinsics(cfg)
+    scene = synth.BoxScene(ground_half_extent=40.0)
+    pw, pb = scene.map_points(ext_R=R, ext_t=t)
+    K, W = max(args.steps, 8), max(args.warmup, 3)
+    n = K + W
+    g = synth.rng(77)
+    # a slow random walk of the true pose; the filter starts at the first true pose
+    rv = np.cumsum(2e-3 * g.standard_normal((n, 3)), 0)
+    tv = np.cumsum(0.01 * g.standard_normal((n, 3)), 0) * np.array([1, 1, 0.1])
+    scans = [scene.scan(rotvec=rv[i], trans=tv[i], ext_R=R, ext_t=t, blind=cfg["blind"], stream=5000 + i, streaming=True,
+                        **synth.VLP16) for i in range(n)]
+    kin_mode = not cfg["only_imu_use"]
+    Q = abi.process_cov_Q(cfg)
+
+    def run(make, label):
+        x = abi.default_states(1); P = abi.init_cov(1); clk = np.zeros(1, abi.CLOCK_DTYPE)
+        clk["last_predict_time"] = 0.0; clk["last_update_time"] = 0.0
+        proc = make()
+        lat, neff = [], []
+        for i, sc in enumerate(scans):
+            t0 = 0.1 * i
+            pts, offs, times = synth.bucketize(sc, begin_time=t0)
+            meas = (synth.kinimu_stream if kin_mode else synth.imu_stream)(t0 - 0.1 if i else -0.005, t0 + 0.1, 400.0, stream=9000 + i)
+            meas = meas[meas["stamp"] > float(clk["last_update_time"][0]) - 1.0]
+            a = time.perf_counter()
+            x, P, clk, ne = proc(x, P, clk, pts, offs, times, meas, t0)
+            lat.append(1e3 * (time.perf_counter() - a)); neff.append(ne)
+        return np.array(lat[W:]), np.array(neff[W:]), x
+
+    def make_gpu():
+        eng = Engine(cfg, device=int(os.environ.get("LOCAL_RANK", "0")))
+        eng.map_build(pw, pb)
+
+        def proc(x, P, clk, pts, offs, times, meas, t0):
+            o = eng.process_scan(x, P, Q, clk, pts, offs, times, imu=None if kin_mode else meas, kin=meas if kin_mode else None,
+                                 gravity=9.81, acc_norm=9.79, iters=1, update_map=True)
+            return o["x"], o["P"].reshape(1, 900), o["clk"], o["n_eff"]
+        return proc
+
+    def make_cpu():
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import lko
+        o = lko.Oracle(cfg)
+        o.build_voxel_map(pw, pb)
+        o.set_options(gain_mode=lko.GAIN_LITERAL, iters=1, update_map=True, imu_mode_only=not kin_mode, gravity=9.81, acc_norm=9.79)
+
+        def proc(x, P, clk, pts, offs, times, meas, t0):
+            o.set_filter(x, P, Q, clk)
+            r = o.process_scan(t0, pts, imu=None if kin_mode else meas, kin=meas if kin_mode else None)
+            xo, Po, _, co = o.get_filter()
+            return xo, Po.reshape(1, 900), co, r["n_eff"]
+        return proc
+
+    impl_ref = args.impl == "reference"
+    lat, neff, x_end = run(make_cpu if impl_ref else make_gpu, "cpu" if impl_ref else "gpu")
+    line = dict(metric="p50 per-scan latency of the streaming ESKF LiDAR update (10 Hz, ~50 buckets/scan, map updated per bucket)",
+                value=float(np.median(lat)), unit="ms", n_gpus=1, steps=K, warmup=W, ms_per_step=float(np.mean(lat)),
+                p95_ms=float(np.percentile(lat, 95)), higher_is_better=False, scaling="weak", vs_baseline=None, dtype="f64",
+                data="synthetic", impl="reference" if impl_ref else "ours",
+                config=dict(workload=args.workload, baseline_config="configs[4]: NCLT-style 10 Hz stream, IMU%s observations, latency mode" % ("+kinematic" if kin_mode else ""),
+                            points_per_scan=int(np.mean([len(s) for s in scans])), buckets_per_scan=51, imu_hz=400, iters=1,
+                            update_map=True, n_eff_mean=float(np.mean(neff)),
+                            note="wall clock around lk_process_scan with host buffers (H2D + D2H + sync inside)" if not impl_ref else
+                                 "CPU restatement (oracle/), literal N x N gain per bucket as the reference, 1 thread"))
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4096)
     ap.add_argument("--warmup", type=int, default=512)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="leg_fusion_b1", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="leg_fusion_b1", choices=sorted(WORKLOADS) + ["nclt_stream", "leg_fusion_stream"])
     ap.add_argument("--scans", type=int, default=0, help="ring size (distinct scans staged in HBM)")
     ap.add_argument("--e2e-steps", type=int, default=256)
     ap.add_argument("--cpu-scans", type=int, default=8)
@@ -167,6 +251,12 @@ def main():
     ap.add_argument("--gather-mode", type=int, default=-1)
     ap.add_argument("--fused", type=int, default=-1, help="0 = force the multi-kernel path for batch-of-one runs")
     args = ap.parse_args()
+    if args.workload.endswith("_stream"):
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        if args.steps == 4096:
+            args.steps, args.warmup = 100, 5
+        return stream_latency(args)
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -275,7 +365,8 @@ def main():
     achieved = alg_bytes_per_launch / (res_ms * 1e-3) / 1e9 if res_ms > 0 else 0.0
     fused = (B == 1 and args.fused != 0)
     roofline = dict(bound="hbm", kernel="k_scan_fused (whole scan: 3 x [residual+reduce+solve] + re-projection)" if fused else "k_residual", achieved=achieved, peak=hbm_peak, unit="GB/s",
-                    frac=achieved / hbm_peak, traffic=None, peak_source=peak_src,
+                    frac=achieved / hbm_peak, traffic=ncu_traffic("k_scan_fused" if fused else "k_residual_stream"),
+                    peak_source=peak_src,
                     alg_bytes_per_launch=alg_bytes_per_launch, avg_launch_us=res_ms * 1e3,
                     share_of_step=tm["residual_ms"] / tm["total_ms"] if tm["total_ms"] > 0 else None)
 
