@@ -677,7 +677,8 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
             ra.chunk_first = c0;
             ra.last_iter = (it == iters - 1) ? 1 : 0;
             if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
-            launch_residual(ra, c1 - c0, false, h->max_chunk_pts <= 256 && (c1 - c0) <= 2 * 148, s);  // latency variant only for small grids
+            launch_residual(ra, c1 - c0, false, count == 1 && h->max_chunk_pts <= 256, s);  // latency variant only for a single scan:
+            // the kernel family must not depend on how a batch is sharded (bitwise-reproducible sums)
             if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
             if (c1 > c0) { ++h->acc_launches; ++h->acc_residual_launches; }
         }

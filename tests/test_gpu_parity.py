@@ -169,3 +169,24 @@ def test_golden_fixtures_on_gpu():
     st = eng.map_stats()
     assert st["roots"] == int(g["n_roots"]) and st["nodes"] >= int(g["n_nodes"]) and st["points"] == int(g["n_points"])
     assert st["planes"] == int(g["n_planes"])
+
+
+def test_batched_results_do_not_depend_on_sharding():
+    """SURVEY §4 multi-GPU invariant: per-scan outputs are bitwise identical however a batch is cut into
+    shards (chunking is a function of the bucket alone, partial sums are added in a fixed order, and every
+    batch of >= 2 scans runs the same kernel family) — and identical from run to run."""
+    from legkilo_b200 import shard
+    cfg, blob, scans = scenes.box_scene(batch=4, stream0=1300)
+    eng = Engine(cfg); eng.map_upload(blob)
+    x0 = abi.default_states(4); P0 = abi.init_cov(4); clk = np.zeros(4, abi.CLOCK_DTYPE); Q = abi.process_cov_Q(cfg)
+    pts = np.concatenate(scans)
+    offs = np.concatenate([[0], np.cumsum([len(s) for s in scans])]).astype(np.uint32)
+    full = eng.scan_update(x0, P0, Q, clk, pts, offs, np.zeros(4), iters=3)
+    again = eng.scan_update(x0, P0, Q, clk, pts, offs, np.zeros(4), iters=3)
+    assert full["x"].tobytes() == again["x"].tobytes() and full["P"].tobytes() == again["P"].tobytes()
+    for rank in range(2):
+        s = shard.shard_batch(rank, 2, x0, P0, clk, pts, offs, np.zeros(4))
+        part = eng.scan_update(s["x"], s["P"], Q, s["clk"], s["pts"], s["scan_offsets"], s["bucket_times"], iters=3)
+        assert part["x"].tobytes() == full["x"][s["lo"]:s["hi"]].tobytes()
+        assert part["P"].tobytes() == full["P"][s["lo"]:s["hi"]].tobytes()
+        assert np.array_equal(part["n_eff"], full["n_eff"][s["lo"]:s["hi"]])
