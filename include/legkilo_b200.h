@@ -296,6 +296,37 @@ int lk_process_scan(lk_handle h, lk_state* x_inout, double* P_inout, const doubl
                     double gravity, double acc_norm, int iters, int update_map,
                     float* pts_world_out, uint32_t* n_effective_out, uint32_t* n_consumed);
 
+/* ---- what feeds the path ------------------------------------------- */
+
+/* Field layout of a sensor_msgs/PointCloud2 as pcl::fromROSMsg resolves it by name for the three
+ * driver formats of legkilo/src/preprocess/lidar_processing.h:10-72. */
+typedef enum lk_lidar_type { LK_LIDAR_VELODYNE = 1, LK_LIDAR_OUSTER = 2, LK_LIDAR_HESAI = 3 } lk_lidar_type;
+typedef struct lk_pc2_layout {
+    uint32_t point_step;    /* bytes per point */
+    uint32_t off_x, off_y, off_z, off_intensity; /* float32 fields */
+    uint32_t off_time;      /* velodyne "time" float32 | ouster "t" uint32 | hesai "timestamp" float64 */
+    int32_t lidar_type;     /* lk_lidar_type: selects the time field's type and arithmetic */
+    int32_t reserved;
+} lk_pc2_layout;
+
+/* LidarProcessing::{velodyne,ouster,hesai}Handler (lidar_processing.cc:25-108): every filter_num-th
+ * point outside the blind sphere, time offset from the first point rounded to 1/500 s into the
+ * `curvature` slot. pts_out: float4 (x, y, z, curvature) x n_points capacity, intensity_out nullable.
+ * first_time / last_time: time_scale x the first / last RAW point's time (the caller adds the header
+ * stamp as lidar_processing.cc:33-34 does). */
+int lk_decode_pointcloud2(lk_handle h, const uint8_t* data, uint32_t n_points, const lk_pc2_layout* layout,
+                          float blind, int32_t filter_num, double time_scale, float* pts_out, float* intensity_out,
+                          uint32_t* n_out, double* first_time, double* last_time);
+
+/* The two steps between decode and the hot loop (KILO.cc:356-378): pcl::VoxelGrid centroid filter with
+ * leaf_size on all axes (PCL 1.8 voxel_grid.hpp: leaf index = floor(p / leaf) - min index, centroid of
+ * x, y, z AND curvature in float, leaves emitted in ascending index), then the sort by curvature
+ * (stable here; std::sort in the reference) and the maximal equal-curvature runs.
+ * Outputs (capacity n_in points / n_in + 1 offsets): pts_out float4, bucket_offsets, bucket_curvature
+ * (add lidar_begin_time_ to get bucket times). */
+int lk_preprocess_scan(lk_handle h, const float* pts_in, uint32_t n_in, float leaf_size, float* pts_out,
+                       uint32_t* n_out, uint32_t* bucket_offsets, float* bucket_curvature, uint32_t* n_buckets);
+
 #ifdef __cplusplus
 }
 #endif

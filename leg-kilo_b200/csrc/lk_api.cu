@@ -9,6 +9,15 @@
 #include "lk_kernels.h"
 #include "lk_mapdev.h"
 
+namespace lk {
+int decode_pointcloud2_device(const uint8_t* h_data, uint32_t n, const lk_pc2_layout& L, float blind, int filter_num,
+                              double time_scale, float* h_pts_out, float* h_intensity_out, uint32_t* n_out, cudaStream_t s,
+                              std::string& err);
+int preprocess_scan_device(const float* h_pts_in, uint32_t n, float leaf, float* h_pts_out, uint32_t* n_out,
+                           uint32_t* h_bucket_offsets, float* h_bucket_curv, uint32_t* n_buckets, cudaStream_t s,
+                           std::string& err);
+}  // namespace lk
+
 using namespace lk;
 
 namespace {
@@ -969,6 +978,44 @@ int lk_process_scan(lk_handle h, lk_state* x_inout, double* P_inout, const doubl
         *n_consumed = c;
     }
     return lk_batch_fetch(h, x_inout, P_inout, clk_inout, pts_world_out, n_effective_out);
+}
+
+int lk_decode_pointcloud2(lk_handle h, const uint8_t* data, uint32_t n_points, const lk_pc2_layout* layout, float blind,
+                          int32_t filter_num, double time_scale, float* pts_out, float* intensity_out, uint32_t* n_out,
+                          double* first_time, double* last_time) {
+    if (!h || !layout || !n_out || (n_points && (!data || !pts_out))) return fail(h, LK_ERR_INVALID_ARG, "null argument");
+    if (filter_num < 1) return fail(h, LK_ERR_INVALID_ARG, "filter_num must be >= 1");
+    const lk_pc2_layout& L = *layout;
+    const uint32_t tsz = L.lidar_type == LK_LIDAR_HESAI ? 8u : 4u;
+    if (L.lidar_type < 1 || L.lidar_type > 3 || L.off_x + 4 > L.point_step || L.off_y + 4 > L.point_step ||
+        L.off_z + 4 > L.point_step || L.off_intensity + 4 > L.point_step || L.off_time + tsz > L.point_step)
+        return fail(h, LK_ERR_INVALID_ARG, "field layout does not fit point_step");
+    cudaSetDevice(h->device);
+    auto host_time = [&](uint32_t i) {
+        const uint8_t* p = data + (size_t)i * L.point_step + L.off_time;
+        if (L.lidar_type == LK_LIDAR_VELODYNE) { float t; std::memcpy(&t, p, 4); return (double)t; }
+        if (L.lidar_type == LK_LIDAR_OUSTER) { uint32_t t; std::memcpy(&t, p, 4); return (double)t; }
+        double t; std::memcpy(&t, p, 8); return t;
+    };
+    if (n_points) {  // lidar_processing.cc:30-31 (float for Velodyne / Ouster, double for Hesai)
+        const double f = time_scale * host_time(0), l = time_scale * host_time(n_points - 1);
+        if (first_time) *first_time = L.lidar_type == LK_LIDAR_HESAI ? f : (double)(float)f;
+        if (last_time) *last_time = L.lidar_type == LK_LIDAR_HESAI ? l : (double)(float)l;
+    }
+    std::string err;
+    int rc = decode_pointcloud2_device(data, n_points, L, blind, filter_num, time_scale, pts_out, intensity_out, n_out, h->stream, err);
+    return rc ? fail(h, rc, err) : LK_OK;
+}
+
+int lk_preprocess_scan(lk_handle h, const float* pts_in, uint32_t n_in, float leaf_size, float* pts_out, uint32_t* n_out,
+                       uint32_t* bucket_offsets, float* bucket_curvature, uint32_t* n_buckets) {
+    if (!h || !n_out || !n_buckets || !bucket_offsets || (n_in && (!pts_in || !pts_out || !bucket_curvature)))
+        return fail(h, LK_ERR_INVALID_ARG, "null argument");
+    if (!(leaf_size > 0)) return fail(h, LK_ERR_INVALID_ARG, "leaf size must be positive");
+    cudaSetDevice(h->device);
+    std::string err;
+    int rc = preprocess_scan_device(pts_in, n_in, leaf_size, pts_out, n_out, bucket_offsets, bucket_curvature, n_buckets, h->stream, err);
+    return rc ? fail(h, rc, err) : LK_OK;
 }
 
 }  // extern "C"

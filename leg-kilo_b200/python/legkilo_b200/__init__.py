@@ -67,6 +67,8 @@ def lib():
         L.lk_obs_kinimu.argtypes = [vp, vp, vp, vp, vp, vp, u32, dbl, dbl]
         L.lk_process_scan.argtypes = [vp, vp, vp, vp, vp, vp, u32, vp, vp, u32, vp, vp, u32, dbl, dbl, i32, i32, vp,
                                       vp, vp]
+        L.lk_decode_pointcloud2.argtypes = [vp, vp, u32, vp, C.c_float, i32, dbl, vp, vp, vp, vp, vp]
+        L.lk_preprocess_scan.argtypes = [vp, vp, u32, C.c_float, vp, vp, vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -287,6 +289,25 @@ class Engine:
         self._chk(lib().lk_process_scan(self.h, _p(x), _p(P), _p(Q), _p(clk), _p(pts), len(pts), _p(bo), _p(bt), len(bt), _p(imu),
                                         _p(kin), nm, gravity, acc_norm, iters, int(update_map), _p(world), _p(neff), _p(ncons)))
         return dict(x=x, P=P, clk=clk, world=world, n_eff=int(neff[0]), n_consumed=int(ncons[0]))
+
+    def decode_pointcloud2(self, data, layout, blind, filter_num, time_scale):
+        """lk_decode_pointcloud2: raw PointCloud2 bytes -> float4 (x, y, z, curvature) + intensity."""
+        data = np.ascontiguousarray(data, np.uint8)
+        n = data.size // layout.point_step
+        pts = np.zeros((n, 4), np.float32); inten = np.zeros(n, np.float32)
+        no = np.zeros(1, np.uint32); ft = np.zeros(1); lt = np.zeros(1)
+        self._chk(lib().lk_decode_pointcloud2(self.h, _p(data), n, C.byref(layout), blind, filter_num, time_scale, _p(pts),
+                                              _p(inten), _p(no), _p(ft), _p(lt)))
+        return pts[:no[0]].copy(), inten[:no[0]].copy(), float(ft[0]), float(lt[0])
+
+    def preprocess_scan(self, pts, leaf):
+        """lk_preprocess_scan: voxel-grid centroid filter, stable curvature sort, bucket boundaries."""
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 4)
+        n = len(pts)
+        out = np.zeros((n, 4), np.float32); offs = np.zeros(n + 1, np.uint32); curv = np.zeros(max(n, 1), np.float32)
+        no = np.zeros(1, np.uint32); nb = np.zeros(1, np.uint32)
+        self._chk(lib().lk_preprocess_scan(self.h, _p(pts), n, leaf, _p(out), _p(no), _p(offs), _p(curv), _p(nb)))
+        return out[:no[0]].copy(), offs[:nb[0] + 1].copy(), curv[:nb[0]].copy()
 
     def predict(self, x, P, Q, dt, prop_state=True, prop_cov=True):
         x = np.array(x, abi.STATE_DTYPE, copy=True); batch = len(x)

@@ -45,6 +45,30 @@ class LkKinImuMeas(C.Structure):
                 ("contact", C.c_int32 * 4), ("acc", C.c_double * 3), ("gyr", C.c_double * 3)]
 
 
+class LkPc2Layout(C.Structure):
+    _fields_ = [("point_step", C.c_uint32), ("off_x", C.c_uint32), ("off_y", C.c_uint32), ("off_z", C.c_uint32),
+                ("off_intensity", C.c_uint32), ("off_time", C.c_uint32), ("lidar_type", C.c_int32), ("reserved", C.c_int32)]
+
+
+# numpy views of the three driver point layouts (lidar_processing.h:10-72; EIGEN_ALIGN16 structs)
+PC2_DTYPES = {
+    1: np.dtype({"names": ["x", "y", "z", "intensity", "time", "ring"], "formats": ["f4", "f4", "f4", "f4", "f4", "u2"],
+                 "offsets": [0, 4, 8, 16, 20, 24], "itemsize": 32}),
+    2: np.dtype({"names": ["x", "y", "z", "intensity", "t", "reflectivity", "ring", "ambient", "range"],
+                 "formats": ["f4", "f4", "f4", "f4", "u4", "u2", "u1", "u2", "u4"], "offsets": [0, 4, 8, 16, 20, 24, 26, 28, 32],
+                 "itemsize": 48}),
+    3: np.dtype({"names": ["x", "y", "z", "intensity", "timestamp", "ring"], "formats": ["f4", "f4", "f4", "f4", "f8", "u2"],
+                 "offsets": [0, 4, 8, 16, 24, 32], "itemsize": 48}),
+}
+
+
+def pc2_layout(lidar_type: int) -> LkPc2Layout:
+    dt = PC2_DTYPES[lidar_type]
+    tname = {1: "time", 2: "t", 3: "timestamp"}[lidar_type]
+    f = dt.fields
+    return LkPc2Layout(dt.itemsize, f["x"][1], f["y"][1], f["z"][1], f["intensity"][1], f[tname][1], lidar_type, 0)
+
+
 STATE_DTYPE = np.dtype([("rot", "f8", (9,)), ("pos", "f8", (3,)), ("vel", "f8", (3,)), ("ba", "f8", (3,)),
                         ("bw", "f8", (3,)), ("grav", "f8", (3,)), ("imu_a", "f8", (3,)), ("imu_w", "f8", (3,)),
                         ("bv", "f8", (3,)), ("contact", "f8", (3,))])

@@ -65,6 +65,10 @@ def lib():
         L.lko_map_import.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.lko_map_num_roots.restype = C.c_uint64
         L.lko_map_num_roots.argtypes = [C.c_void_p]
+        L.lko_decode_pointcloud2.restype = C.c_uint32
+        L.lko_decode_pointcloud2.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_float, C.c_int, C.c_double] + [C.c_void_p] * 4
+        L.lko_preprocess_scan.restype = C.c_int
+        L.lko_preprocess_scan.argtypes = [C.c_void_p, C.c_uint32, C.c_float] + [C.c_void_p] * 5
         L.lko_batch_run.restype = C.c_double
         L.lko_batch_run.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_int] * 3 + [C.c_void_p] * 3
     return _LIB
@@ -240,3 +244,24 @@ def log_so3(R):
     out = np.zeros(3)
     lib().lko_log(_p(R), _p(out))
     return out
+
+
+def decode_pointcloud2(data, layout, blind, filter_num, time_scale):
+    """lidar_processing.cc:25-108 on a raw PointCloud2 byte buffer; layout = abi.LkPc2Layout."""
+    data = np.ascontiguousarray(data, np.uint8)
+    n = data.size // layout.point_step
+    pts = np.zeros((n, 4), np.float32); inten = np.zeros(n, np.float32)
+    ft = np.zeros(1); lt = np.zeros(1)
+    m = lib().lko_decode_pointcloud2(_p(data), n, C.byref(layout), blind, filter_num, time_scale, _p(pts), _p(inten), _p(ft), _p(lt))
+    return pts[:m].copy(), inten[:m].copy(), float(ft[0]), float(lt[0])
+
+
+def preprocess_scan(pts, leaf):
+    """pcl::VoxelGrid centroid filter + stable curvature sort + equal-curvature runs (KILO.cc:356-378)."""
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 4)
+    n = len(pts)
+    out = np.zeros((n, 4), np.float32); offs = np.zeros(n + 1, np.uint32); curv = np.zeros(max(n, 1), np.float32)
+    no = np.zeros(1, np.uint32); nb = np.zeros(1, np.uint32)
+    rc = lib().lko_preprocess_scan(_p(pts), n, leaf, _p(out), _p(no), _p(offs), _p(curv), _p(nb))
+    assert rc == 0
+    return out[:no[0]].copy(), offs[:nb[0] + 1].copy(), curv[:nb[0]].copy()

@@ -2,7 +2,10 @@
 // restatement in lko_core.cpp. Uses the product's POD structs (include/legkilo_b200.h) so that
 // tests can hand identical buffers to the oracle and to the CUDA library.
 #include <algorithm>
+#include <array>
+#include <cfloat>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <thread>
 
@@ -493,6 +496,115 @@ double lko_batch_run(void* h, int batch, const lk_state* x_in, const double* P_i
     }
     auto t1 = std::chrono::steady_clock::now();
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"
+
+// ============================ what feeds the path ==========================
+#include <climits>
+extern "C" {
+
+// LidarProcessing::{velodyne,ouster,hesai}Handler — legkilo/src/preprocess/lidar_processing.cc:25-108.
+// Returns the number of points kept. pts_out = float4 (x, y, z, curvature).
+uint32_t lko_decode_pointcloud2(const uint8_t* data, uint32_t n, const lk_pc2_layout* L, float blind, int filter_num,
+                                double time_scale, float* pts_out, float* intensity_out, double* first_time,
+                                double* last_time) {
+    if (!n) return 0;
+    auto f32 = [&](uint32_t i, uint32_t off) { float v; std::memcpy(&v, data + (size_t)i * L->point_step + off, 4); return v; };
+    uint32_t m = 0;
+    if (L->lidar_type == LK_LIDAR_HESAI) {
+        auto ts = [&](uint32_t i) { double v; std::memcpy(&v, data + (size_t)i * L->point_step + L->off_time, 8); return v; };
+        double first_point_time = time_scale * ts(0);
+        double last_point_time = time_scale * ts(n - 1);
+        if (first_time) *first_time = first_point_time;
+        if (last_time) *last_time = last_point_time;
+        for (uint32_t i = 0; i < n; ++i) {
+            float x = f32(i, L->off_x), y = f32(i, L->off_y), z = f32(i, L->off_z);
+            if ((i % filter_num) || (blind * blind > x * x + y * y + z * z)) continue;
+            double cur_point_time = time_scale * ts(i);
+            float curvature = std::round((cur_point_time - first_point_time) * 500.0f) / 500.0f;
+            pts_out[4 * m] = x; pts_out[4 * m + 1] = y; pts_out[4 * m + 2] = z; pts_out[4 * m + 3] = curvature;
+            if (intensity_out) intensity_out[m] = f32(i, L->off_intensity);
+            ++m;
+        }
+        return m;
+    }
+    auto ts = [&](uint32_t i) -> double {
+        if (L->lidar_type == LK_LIDAR_VELODYNE) return (double)f32(i, L->off_time);
+        uint32_t v; std::memcpy(&v, data + (size_t)i * L->point_step + L->off_time, 4); return (double)v;
+    };
+    float first_point_time = time_scale * ts(0);
+    float last_point_time = time_scale * ts(n - 1);
+    if (first_time) *first_time = first_point_time;
+    if (last_time) *last_time = last_point_time;
+    for (uint32_t i = 0; i < n; ++i) {
+        float x = f32(i, L->off_x), y = f32(i, L->off_y), z = f32(i, L->off_z);
+        if ((i % filter_num) || (blind * blind > x * x + y * y + z * z)) continue;
+        float cur_point_time = time_scale * ts(i);
+        float curvature = std::round((cur_point_time - first_point_time) * 500.0f) / 500.0f;
+        pts_out[4 * m] = x; pts_out[4 * m + 1] = y; pts_out[4 * m + 2] = z; pts_out[4 * m + 3] = curvature;
+        if (intensity_out) intensity_out[m] = f32(i, L->off_intensity);
+        ++m;
+    }
+    return m;
+}
+
+// pcl::VoxelGrid<PointXYZINormal>::applyFilter (PCL 1.8 voxel_grid.hpp; the library is absent, its
+// published algorithm is restated: leaf index = floor(p * inverse_leaf) - min_b, dot divb_mul; centroid
+// of x, y, z and curvature as float sums / float(n); leaves in ascending index) as KILO::process calls
+// it (KILO.cc:356-360), then the sort by curvature (stable: canonical order) and the equal-curvature runs
+// (KILO.cc:370-378). Returns -1 when the leaf size is too small for the extent (PCL only warns).
+int lko_preprocess_scan(const float* in, uint32_t n, float leaf, float* out, uint32_t* n_out, uint32_t* bucket_offsets,
+                        float* bucket_curv, uint32_t* n_buckets) {
+    *n_out = 0; *n_buckets = 0; bucket_offsets[0] = 0;
+    if (!n) return 0;
+    float inv = 1.0f / leaf;
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* p = in + 4 * i;
+        if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+        for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], p[k]); mx[k] = std::max(mx[k], p[k]); }
+    }
+    int min_b[3], max_b[3], div_b[3];
+    for (int k = 0; k < 3; ++k) {
+        min_b[k] = (int)std::floor(mn[k] * inv);
+        max_b[k] = (int)std::floor(mx[k] * inv);
+        div_b[k] = max_b[k] - min_b[k] + 1;
+    }
+    if ((long long)div_b[0] * div_b[1] * div_b[2] > (long long)INT_MAX) return -1;
+    const int mul[3] = {1, div_b[0], div_b[0] * div_b[1]};
+    std::vector<std::pair<int, uint32_t>> idx;
+    idx.reserve(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* p = in + 4 * i;
+        if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+        int i0 = (int)std::floor(p[0] * inv) - min_b[0], i1 = (int)std::floor(p[1] * inv) - min_b[1],
+            i2 = (int)std::floor(p[2] * inv) - min_b[2];
+        idx.push_back({i0 * mul[0] + i1 * mul[1] + i2 * mul[2], i});
+    }
+    std::stable_sort(idx.begin(), idx.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    std::vector<std::array<float, 4>> cent;
+    for (size_t a = 0; a < idx.size();) {
+        size_t b = a;
+        float s[4] = {0, 0, 0, 0};
+        while (b < idx.size() && idx[b].first == idx[a].first) {
+            for (int k = 0; k < 4; ++k) s[k] += in[4 * idx[b].second + k];
+            ++b;
+        }
+        float fn = (float)(b - a);
+        cent.push_back({s[0] / fn, s[1] / fn, s[2] / fn, s[3] / fn});
+        a = b;
+    }
+    std::stable_sort(cent.begin(), cent.end(), [](const auto& a, const auto& b) { return a[3] < b[3]; });
+    uint32_t nb = 0;
+    for (size_t i = 0; i < cent.size(); ++i) {
+        std::memcpy(out + 4 * i, cent[i].data(), 16);
+        if (i == 0 || cent[i][3] != cent[i - 1][3]) { bucket_offsets[nb] = (uint32_t)i; bucket_curv[nb] = cent[i][3]; ++nb; }
+    }
+    bucket_offsets[nb] = (uint32_t)cent.size();
+    *n_out = (uint32_t)cent.size();
+    *n_buckets = nb;
+    return 0;
 }
 
 }  // extern "C"
