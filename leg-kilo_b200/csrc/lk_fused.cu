@@ -72,9 +72,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
     FT(0);
 
     // the filter: reload from the staged inputs (idempotent runs)
-    for (int e = tid; e < 900; e += BLOCK) sm->f.P[e] = a.P_in[(size_t)scan * 900 + e];
-    if (tid < 36) sm->f.x[tid] = a.x_in[(size_t)scan * 36 + tid];
-    if (tid < 2) sm->clk[tid] = reinterpret_cast<const double*>(a.clk_in + scan)[tid];
+    {
+        const double* Pin = a.inline_in ? a.inl.P : a.P_in + (size_t)scan * 900;
+        const double* xin = a.inline_in ? a.inl.x : a.x_in + (size_t)scan * 36;
+        const double* cin = a.inline_in ? a.inl.clk : reinterpret_cast<const double*>(a.clk_in + scan);
+        for (int e = tid; e < 900; e += BLOCK) sm->f.P[e] = Pin[e];
+        if (tid < 36) sm->f.x[tid] = xin[tid];
+        if (tid < 2) sm->clk[tid] = cin[tid];
+    }
     pass_init<BLOCK>(&sm->u.pass);
     FT(1);
     uint32_t n_eff_total = 0;
@@ -85,8 +90,16 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
     uint32_t mi = 0;  // next inertial / kinematic sample
 
     for (uint32_t k = 0; k < a.n_steps; ++k) {
-        const StepInit in = a.inits[(size_t)k * a.batch + scan];
+        const StepInit in = a.inline_in ? a.inl.steps[k] : a.inits[(size_t)k * a.batch + scan];
         if (!in.active) continue;
+        // with one chunk per block a lane sees the same point in every iteration of the bucket: issue its
+        // load now, ahead of the predict (the point may sit in page-locked host memory)
+        const bool one_chunk = a.lane_cache && (in.chunk_end - in.chunk_begin) <= gridDim.x;
+        float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (one_chunk) {
+            const uint32_t q = in.pt_begin + blockIdx.x * (uint32_t)BLOCK + (uint32_t)tid;
+            if (blockIdx.x < in.chunk_end - in.chunk_begin && q < in.pt_end) pre = __ldg(a.pts + q);
+        }
         // 0) every queued inertial / kinematic sample older than this bucket (KILO.cc:379-390)
         bool drained = false;
         while (mi < a.n_meas) {
@@ -123,8 +136,6 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
         if (tid == 0) sm->clk[0] = in.t_bucket;
         bool updated = false;
         uint32_t n_last = 0;
-        // with one chunk per block a lane sees the same point in every iteration of the bucket
-        const bool one_chunk = a.lane_cache && (in.chunk_end - in.chunk_begin) <= gridDim.x;
         LaneCache lc;
         lc.have = 0;
         const uint32_t n_chunks = in.chunk_end - in.chunk_begin;
@@ -134,14 +145,16 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
             double* partial = a.partial + (size_t)(it_global & 1) * a.partial_stride;
             // 2) residual rows of my chunks -> one partial row per chunk
             for (uint32_t c = in.chunk_begin + blockIdx.x; c < in.chunk_end; c += gridDim.x) {
-                const ChunkDesc cd = a.chunks[c];
+                ChunkDesc cd;  // chunks of a bucket are BLOCK points each (the host stages them the same way)
+                cd.start = in.pt_begin + (c - in.chunk_begin) * (uint32_t)BLOCK;
+                cd.count = min((uint32_t)BLOCK, in.pt_end - cd.start);
                 double acc[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) acc[i] = 0.0;
                 unsigned long long* ptr = (a.trace && it_global == 1) ? a.trace + (size_t)(gridDim.x + blockIdx.x) * 64 : nullptr;
                 if (one_chunk)
                     block_points_pass<BLOCK, false, true>(&sm->u.pass, phase, a.pts + cd.start, cd.count, (size_t)cd.start,
-                                                          sm->sc, a.mv, a.g, acc, dbg, lc, ptr);
+                                                          sm->sc, a.mv, a.g, acc, dbg, lc, ptr, pre);
                 else
                     block_points_pass<BLOCK, false, false>(&sm->u.pass, phase, a.pts + cd.start, cd.count, (size_t)cd.start,
                                                            sm->sc, a.mv, a.g, acc, dbg, lc, ptr);
@@ -179,13 +192,20 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
         const float inten = updated ? 255.0f : 0.0f;
         const Globals& g = a.g;
         for (uint32_t c = in.chunk_begin + blockIdx.x; c < in.chunk_end; c += gridDim.x) {
-            const ChunkDesc cd = a.chunks[c];
+            ChunkDesc cd;
+            cd.start = in.pt_begin + (c - in.chunk_begin) * (uint32_t)BLOCK;
+            cd.count = min((uint32_t)BLOCK, in.pt_end - cd.start);
             if ((uint32_t)tid < cd.count) {
-                float4 pt = __ldg(a.pts + cd.start + tid);
-                double bx = pt.x, by = pt.y, bz = pt.z;
-                double pix = g.Re[0] * bx + g.Re[1] * by + g.Re[2] * bz + g.te[0];
-                double piy = g.Re[3] * bx + g.Re[4] * by + g.Re[5] * bz + g.te[1];
-                double piz = g.Re[6] * bx + g.Re[7] * by + g.Re[8] * bz + g.te[2];
+                double pix, piy, piz;
+                if (one_chunk && lc.have) {  // the lane's own point, already in the IMU frame
+                    pix = lc.pix; piy = lc.piy; piz = lc.piz;
+                } else {
+                    float4 pt = __ldg(a.pts + cd.start + tid);
+                    double bx = pt.x, by = pt.y, bz = pt.z;
+                    pix = g.Re[0] * bx + g.Re[1] * by + g.Re[2] * bz + g.te[0];
+                    piy = g.Re[3] * bx + g.Re[4] * by + g.Re[5] * bz + g.te[1];
+                    piz = g.Re[6] * bx + g.Re[7] * by + g.Re[8] * bz + g.te[2];
+                }
                 const double* X = sm->f.x;
                 float4 o;
                 o.x = (float)(X[0] * pix + X[1] * piy + X[2] * piz + X[9]);
@@ -224,9 +244,18 @@ int fused_max_blocks(int device) {
     return n;
 }
 
-cudaError_t launch_scan_fused(const FusedArgs& a, uint32_t grid, cudaStream_t s) {
-    void* params[] = {(void*)&a};
-    return cudaLaunchCooperativeKernel((const void*)k_scan_fused, dim3(grid), dim3(BLOCK), params, sizeof(FusedSmem), s);
+// `cooperative` = go through cudaLaunchCooperativeKernel (the driver checks co-residency and serialises
+// cooperative grids: ~10 us between back-to-back launches). The plain launch relies on the same fact the
+// host already enforces — grid <= fused_max_blocks(), i.e. every block fits on the device at once — so the
+// blocks spinning on the grid barrier can only ever wait for blocks that are resident or that become
+// resident as soon as unrelated work drains; nothing they wait for depends on them.
+cudaError_t launch_scan_fused(const FusedArgs& a, uint32_t grid, cudaStream_t s, bool cooperative) {
+    if (cooperative) {
+        void* params[] = {(void*)&a};
+        return cudaLaunchCooperativeKernel((const void*)k_scan_fused, dim3(grid), dim3(BLOCK), params, sizeof(FusedSmem), s);
+    }
+    k_scan_fused<<<dim3(grid), dim3(BLOCK), sizeof(FusedSmem), s>>>(a);
+    return cudaGetLastError();
 }
 
 }  // namespace lk

@@ -87,8 +87,17 @@ void launch_update_by_points(double* x, double* P, uint32_t n, const double* h, 
                              cudaStream_t s);
 
 // ---- fused per-scan persistent kernel (lk_fused.cu) -------------------------------------------
+constexpr int FUSED_INLINE_STEPS = 64;
+// Small inputs carried in the kernel's parameter block (no staging copy before the launch).
+struct FusedInline {
+    double x[36];
+    double P[900];
+    double clk[2];
+    StepInit steps[FUSED_INLINE_STEPS];
+};
+
 struct FusedArgs {
-    const float4* pts;
+    const float4* pts;    // device memory, or page-locked host memory read in place (each point is read once)
     float4* world;
     const ChunkDesc* chunks;
     const StepInit* inits;  // [n_steps][batch]
@@ -117,9 +126,11 @@ struct FusedArgs {
     lk_eskf_cfg ecfg;
     unsigned long long* trace;  // optional: 32 %globaltimer stamps per block
     Globals g;
+    int inline_in;  // x_in / P_in / clk_in / inits come from `inl`
+    FusedInline inl;
 };
 size_t fused_smem_bytes();
 int fused_max_blocks(int device);
-cudaError_t launch_scan_fused(const FusedArgs& a, uint32_t grid, cudaStream_t s);
+cudaError_t launch_scan_fused(const FusedArgs& a, uint32_t grid, cudaStream_t s, bool cooperative);
 
 }  // namespace lk

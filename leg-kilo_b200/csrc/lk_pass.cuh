@@ -133,7 +133,8 @@ template <int NTHREADS, bool DEBUG, bool CACHED>
 __device__ __forceinline__ void block_points_pass(PassSmem<NTHREADS>* ps, uint32_t& phase, const float4* __restrict__ pts,
                                                   uint32_t count, size_t base_idx, const ScanConst& sc, const MapView& mv,
                                                   const Globals& g, double (&acc)[32], const DebugRows& dbg, LaneCache& lc,
-                                                  unsigned long long* tr = nullptr) {
+                                                  unsigned long long* tr = nullptr,
+                                                  float4 pre = make_float4(0.f, 0.f, 0.f, 0.f)) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #define PT(slot) do { if (tr && (tid & 31) == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); tr[(tid >> 5) * 8 + (slot)] = t_; } } while (0)
     PT(0);
@@ -144,7 +145,7 @@ __device__ __forceinline__ void block_points_pass(PassSmem<NTHREADS>* ps, uint32
     bool need_gather = false;
     if (active) {
         if (!CACHED || lc.have == 0) {
-            const float4 pt = __ldg(pts + tid);
+            const float4 pt = CACHED ? pre : __ldg(pts + tid);  // CACHED: the caller loaded this lane's point
             const double bx = (double)pt.x, by = (double)pt.y, bz = (double)pt.z;
             pc.pix = g.Re[0] * bx + g.Re[1] * by + g.Re[2] * bz + g.te[0];
             pc.piy = g.Re[3] * bx + g.Re[4] * by + g.Re[5] * bz + g.te[1];

@@ -190,13 +190,21 @@ class Engine:
         return x, P, clk, pts, scan_offsets, scan_bucket_ptr, bucket_offsets, bucket_times
 
     def scan_update(self, x, P, Q, clk, pts, scan_offsets, bucket_times, scan_bucket_ptr=None, bucket_offsets=None,
-                    iters=1, update_map=False, want_world=True):
-        """lk_scan_update: host buffers in, host buffers out (copies of x / P / clk are returned)."""
+                    iters=1, update_map=False, want_world=True, pinned=False):
+        """lk_scan_update: host buffers in, host buffers out (copies of x / P / clk are returned).
+        pinned=True puts the points and the world cloud in page-locked memory (lk_host_alloc), which lets a
+        one-scan call run in direct mode (the kernel reads / writes them in place)."""
         x, P, clk, pts, so, sbp, bo, bt = self._norm_batch(x, P, clk, pts, scan_offsets, scan_bucket_ptr,
                                                            bucket_offsets, bucket_times)
         x = x.copy(); P = P.copy(); clk = clk.copy()
         Q = np.ascontiguousarray(Q, np.float64)
-        world = np.zeros((len(pts), 4), np.float32) if want_world else None
+        if pinned:
+            hp = pinned_empty(pts.shape, np.float32); hp[...] = pts; pts = hp
+            world = pinned_empty((len(pts), 4), np.float32) if want_world else None
+            if world is not None:
+                world[...] = 0
+        else:
+            world = np.zeros((len(pts), 4), np.float32) if want_world else None
         neff = np.zeros(len(x), np.uint32)
         self._chk(lib().lk_scan_update(self.h, len(x), _p(x), _p(P), _p(Q), _p(clk), _p(pts), _p(so), _p(sbp), _p(bo),
                                        _p(bt), iters, int(update_map), _p(world), _p(neff)))

@@ -92,6 +92,52 @@ def test_single_scan_paths_agree_with_oracle(fused):
     globals()[key] = out
 
 
+@pytest.mark.parametrize("streaming", [False, True])
+def test_direct_io_matches_staged_bitwise(streaming):
+    """One scan through lk_scan_update with page-locked caller buffers runs in direct mode (points read in
+    place, world cloud / filter stored in place, small inputs in the kernel parameter block). Same kernel, same
+    arithmetic: every output must equal the staged path's bit for bit."""
+    cfg, blob, scans = scenes.box_scene(batch=1, streaming=streaming, stream0=300)
+    if streaming:
+        pts, offs, times = synth.bucketize(scans[0], begin_time=100.0)
+        x0 = _moving_state()
+        clk0 = np.zeros(1, abi.CLOCK_DTYPE); clk0["last_predict_time"] = 99.99; clk0["last_update_time"] = 99.985
+    else:
+        pts, offs, times = scans[0], np.array([0, len(scans[0])], np.uint32), np.zeros(1)
+        x0 = abi.default_states(1); clk0 = np.zeros(1, abi.CLOCK_DTYPE)
+    P0 = abi.init_cov(1); Q = abi.process_cov_Q(cfg)
+    eng = Engine(cfg)
+    eng.map_upload(blob)
+    kw = dict(scan_bucket_ptr=[0, len(times)], bucket_offsets=offs, iters=2)
+    outs = {}
+    for name, params, pinned in (("staged", dict(direct_io=0), True), ("pageable", dict(direct_io=1), False),
+                                 ("direct", dict(direct_io=1, inline_in=0), True), ("direct+inline", dict(direct_io=1, inline_in=1), True)):
+        for k, v in params.items():
+            eng.set_param(k, v)
+        outs[name] = eng.scan_update(x0, P0, Q, clk0, pts, [0, len(pts)], times, pinned=pinned, **kw)
+        # a second call re-uses the cached process noise
+        again = eng.scan_update(x0, P0, Q, clk0, pts, [0, len(pts)], times, pinned=pinned, **kw)
+        np.testing.assert_array_equal(again["P"], outs[name]["P"])
+    ref = outs["staged"]
+    assert int(ref["n_eff"][0]) > 0
+    for name, o in outs.items():
+        np.testing.assert_array_equal(o["x"].view(np.float64), ref["x"].view(np.float64), err_msg=name)
+        np.testing.assert_array_equal(o["P"], ref["P"], err_msg=name)
+        np.testing.assert_array_equal(o["clk"].view(np.float64), ref["clk"].view(np.float64), err_msg=name)
+        np.testing.assert_array_equal(o["n_eff"], ref["n_eff"], err_msg=name)
+        np.testing.assert_array_equal(np.asarray(o["world"]), np.asarray(ref["world"]), err_msg=name)
+    # a changed process noise must be picked up by the cached copy
+    Q2 = Q * 2.0
+    eng.set_param("direct_io", 1); eng.set_param("inline_in", 1)
+    a = eng.scan_update(x0, P0, Q2, clk0, pts, [0, len(pts)], times, pinned=True, **kw)
+    eng.set_param("direct_io", 0)
+    b = eng.scan_update(x0, P0, Q2, clk0, pts, [0, len(pts)], times, pinned=True, **kw)
+    eng.set_param("direct_io", 1)
+    np.testing.assert_array_equal(a["P"], b["P"])
+    if streaming:
+        assert not np.array_equal(a["P"], ref["P"])
+
+
 def _oracle_stream(cfg, blob, pts_sorted, begin_time, x0, P0, clk0, iters=1, update_map=False, gain=lko.GAIN_INFORMATION,
                    imu=None, kin=None, imu_mode_only=True):
     o = lko.Oracle(cfg)
