@@ -107,7 +107,11 @@ struct lk_context {
     uint32_t fused_launches = 0;
     // direct mode of lk_scan_update (one scan, page-locked caller buffers): the kernel reads the points and
     // writes the world cloud / the filter in place, the small inputs ride in the kernel's parameter block
-    int direct_io = 1, inline_in = 1, coop_launch = 0;
+    int direct_io = 1, inline_in = 1, coop_launch = 0, n_sms = 148, ws_debug = 0;
+    // throughput family's residual kernel: 2 = double-buffered stream (default), 1 = warp-specialised persistent,
+    // 0 = single-stage stream with the in-kernel tail
+    int use_ws = 2;
+    PinnedBuf h_wdbg;
     bool direct = false, direct_ran = false, inline_ok = false;
     const float4* direct_pts = nullptr;
     float4* direct_world = nullptr;
@@ -185,8 +189,8 @@ void fill_globals(lk_context* c, const double* extR, const double* extT) {
 //     chunks, one per SM); larger ones 2 048-point chunks streamed by warps;
 //   throughput family (>= 2 scans per call): 2 048-point chunks as soon as a bucket exceeds one of them —
 //     every warp then streams 8 groups and the per-chunk reduce / ticket is amortised.
-uint32_t chunk_size_for(uint32_t n, bool throughput) {
-    if (throughput) return n <= 2048u ? 256u : 2048u;
+uint32_t chunk_size_for(uint32_t n, bool throughput, uint32_t big = 2048u) {
+    if (throughput) return n <= 2048u ? 256u : big;
     return n <= 65536u ? 256u : 2048u;
 }
 
@@ -216,6 +220,7 @@ ResidualArgs residual_args(lk_context* c, const ChunkDesc* chunks) {
     a.clk = c->clk.as<lk_stream_clock>();
     a.n_eff = c->n_eff.as<uint32_t>();
     a.trace = c->trace_on ? c->trace.as<unsigned long long>() : nullptr;
+    a.wdbg = c->ws_debug ? (unsigned long long*)c->h_wdbg.p : nullptr;
     a.g = c->g;
     return a;
 }
@@ -250,6 +255,7 @@ int lk_create(const lk_eskf_cfg* eskf_cfg, const lk_map_cfg* map_cfg, const doub
     c->ec = *eskf_cfg;
     c->mc = *map_cfg;
     fill_globals(c, ext_rot, ext_t);
+    cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device);
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete c;
@@ -321,6 +327,15 @@ int lk_set_param(lk_handle h, const char* name, double value) {
     if (!std::strcmp(name, "kernel_timing")) { h->kernel_timing = (int)value; return LK_OK; }
     if (!std::strcmp(name, "fused")) { h->use_fused = (int)value; return LK_OK; }
     if (!std::strcmp(name, "lane_cache")) { h->lane_cache = (int)value; return LK_OK; }
+    if (!std::strcmp(name, "ws_debug")) {
+        h->ws_debug = (int)value;
+        if (h->ws_debug) {
+            if (h->h_wdbg.ensure(256 * 16 * 8 * 8) != cudaSuccess) return LK_ERR_OUT_OF_MEMORY;
+            std::memset(h->h_wdbg.p, 0, 256 * 16 * 8 * 8);
+        }
+        return LK_OK;
+    }
+    if (!std::strcmp(name, "ws")) { h->use_ws = (int)value; return LK_OK; }
     if (!std::strcmp(name, "coop_launch")) { h->coop_launch = (int)value; return LK_OK; }
     if (!std::strcmp(name, "direct_io")) { h->direct_io = (int)value; return LK_OK; }
     if (!std::strcmp(name, "inline_in")) { h->inline_in = (int)value; return LK_OK; }
@@ -339,6 +354,11 @@ int lk_set_param(lk_handle h, const char* name, double value) {
 // Debug read-back of internal device buffers: what = 0 partial sums, 1 scan constants.
 int lk_debug_read(lk_handle h, int what, void* dst, size_t bytes) {
     if (!h || !dst) return LK_ERR_INVALID_ARG;
+    if (what == 4) {  // debug records of the warp-specialised kernel (page-locked: readable while it runs)
+        if (!h->h_wdbg.p) return LK_ERR_NOT_READY;
+        std::memcpy(dst, h->h_wdbg.p, std::min(bytes, (size_t)256 * 16 * 8 * 8));
+        return LK_OK;
+    }
     if (what == 3) {  // host-side phase times of lk_scan_update (ns, accumulated) — reading resets them
         std::memcpy(dst, h->hprof, std::min(bytes, sizeof(h->hprof)));
         std::memset(h->hprof, 0, sizeof(h->hprof));
@@ -451,6 +471,8 @@ static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P
                 return fail(h, LK_ERR_INVALID_ARG, "bucket_offsets outside their scan");
         }
     }
+    // 60 groups split evenly over the double-buffered kernel's 6 (or 5) warps; 64 over the others' 8
+    const uint32_t big_chunk = h->use_ws >= 2 ? 1920u : 2048u;
     auto build_tables = [&](bool throughput, std::vector<ChunkDesc>& chunks, std::vector<StepInit>& inits) {
         chunks.clear();
         inits.assign((size_t)max_buckets * batch, StepInit());
@@ -468,7 +490,7 @@ static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P
                 in.pt_end = p1;
                 in.t_bucket = bucket_times[b];
                 in.chunk_begin = (uint32_t)chunks.size();
-                uint32_t cs = chunk_size_for(p1 - p0, throughput);
+                uint32_t cs = chunk_size_for(p1 - p0, throughput, big_chunk);
                 for (uint32_t q = p0; q < p1; q += cs) {
                     ChunkDesc cd;
                     cd.scan = (uint32_t)s;
@@ -489,7 +511,7 @@ static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P
     if (batch >= 2) {
         for (uint32_t b = 0; b < scan_bucket_ptr[batch] && !twoTables; ++b) {
             const uint32_t n = bucket_offsets[b + 1] - bucket_offsets[b];
-            twoTables = chunk_size_for(n, true) != chunk_size_for(n, false);
+            twoTables = chunk_size_for(n, true, big_chunk) != chunk_size_for(n, false);
         }
     }
     if (twoTables) build_tables(true, chunksL, h->h_initsL);
@@ -788,8 +810,16 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
             ra.chunk_first = c0;
             ra.last_iter = (it == iters - 1) ? 1 : 0;
             if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
-            launch_residual(ra, c1 - c0, false, count == 1 && h->max_chunk_pts <= 256, s);  // latency variant only for a single scan:
-            // the kernel family must not depend on how a batch is sharded (bitwise-reproducible sums)
+            // latency variant only for a single scan: the kernel family must not depend on how a batch is
+            // sharded (bitwise-reproducible sums)
+            if (count >= 2 && h->use_ws) {
+                if (h->use_ws >= 2) launch_residual_stream2(ra, c1 - c0, s);
+                else launch_residual_ws(ra, c1 - c0, h->n_sms, s);
+                launch_scan_tail(ra, first, count, s);
+                if (c1 > c0) ++h->acc_launches;
+            } else {
+                launch_residual(ra, c1 - c0, false, count == 1 && h->max_chunk_pts <= 256, s);
+            }
             if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
             if (c1 > c0) { ++h->acc_launches; ++h->acc_residual_launches; }
         }

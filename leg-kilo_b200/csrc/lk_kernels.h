@@ -39,11 +39,17 @@ struct ResidualArgs {
     double* dbg_R;
     int32_t* dbg_key;
     unsigned long long* trace;  // optional %globaltimer stamps: 8 per block + 8 for the tail
+    unsigned long long* wdbg;   // optional page-locked debug records of the warp-specialised kernel (16 x 4 per block)
     Globals g;
 };
 
 // single: every chunk of the launch holds at most 128 points (one point per thread)
 void launch_residual(const ResidualArgs& a, uint32_t n_chunks, bool debug, bool single, cudaStream_t s);
+// throughput family: warp-specialised persistent residual pass (lk_stream_ws.cu) writing one partial row per
+// chunk, then the per-scan solve for scans [scan_first, scan_first + n_scans) (lk_residual.cu)
+void launch_residual_ws(const ResidualArgs& a, uint32_t n_chunks, int n_sms, cudaStream_t s);
+void launch_residual_stream2(const ResidualArgs& a, uint32_t n_chunks, cudaStream_t s);  // lk_stream2.cu
+void launch_scan_tail(const ResidualArgs& a, uint32_t scan_first, uint32_t n_scans, cudaStream_t s);
 
 struct PredictArgs {
     const StepInit* init;  // [batch] for this step

@@ -188,7 +188,27 @@ __global__ void __launch_bounds__(BLOCK, 2) k_residual_stream(const __grid_const
     }
 }
 
+// The per-scan solve on its own (after lk_stream_ws.cu's residual pass): one block per scan.
+__global__ void __launch_bounds__(BLOCK) k_scan_tail(const __grid_constant__ ResidualArgs a, const uint32_t scan_first) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    TailSmem* ts = reinterpret_cast<TailSmem*>(s_raw);
+    const uint32_t scan = scan_first + blockIdx.x;
+    const ScanStep st = a.step[scan];
+    if (!st.active || st.chunk_end == st.chunk_begin) return;
+    scan_solve(a, scan, ts);
+}
+
 }  // namespace
+
+void launch_scan_tail(const ResidualArgs& a, uint32_t scan_first, uint32_t n_scans, cudaStream_t s) {
+    if (n_scans == 0) return;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_scan_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem));
+        attr = true;
+    }
+    k_scan_tail<<<n_scans, BLOCK, sizeof(TailSmem), s>>>(a, scan_first);
+}
 
 void launch_residual(const ResidualArgs& a, uint32_t n_chunks, bool debug, bool single, cudaStream_t s) {
     if (n_chunks == 0) return;

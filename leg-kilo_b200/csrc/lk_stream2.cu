@@ -1,0 +1,207 @@
+// lk_stream2.cu — throughput family of the residual pass, double-buffered: every warp streams its 32-point
+// groups of the block's chunk through a 3-deep software pipeline
+//     points(i+3) | key + root-table probe(i+2) | record gather(i+1) -> shared stage | gates + row(i)
+// so that, while a group is evaluated from shared memory (voxel_map.cc:363-411, KILO.cc:187-210), the next
+// group's 32 plane records are already in flight (16 cooperative 16-byte async copies, two records per warp
+// instruction) and the one after has its probe and its points in flight. 6 warps x 2 stages per block,
+// 2 blocks per SM, 168 registers (no spills). Points that fail at their home plane are listed per warp
+// (ballot order) and finished by the whole block in warp-major order with the full reference sequence
+// (KILO.cc:156-178), so the per-chunk sums are bitwise reproducible. One partial row per chunk; the per-scan
+// solve follows as its own kernel (lk_residual.cu: k_scan_tail).
+#include <algorithm>
+
+#include "lk_kernels.h"
+#include "lk_pass.cuh"
+
+namespace lk {
+
+namespace {
+
+constexpr int S2_MAXPTS = 2048;  // largest chunk lk_api.cu hands out
+constexpr int S2_STAGE_BYTES = 32 * TILE_STRIDE;
+// slot of a lane: bytes 0..239 of the plane record (fields end at 232) | root index at 240 | point at 256
+constexpr int S2_SLOT_ROOT = 240, S2_SLOT_PT = 256;
+static_assert(TILE_STRIDE == 272, "slot layout");
+
+template <int S2_WARPS>
+struct S2Smem {
+    static constexpr int FB_CAP = ((S2_MAXPTS / 32 + S2_WARPS - 1) / S2_WARPS) * 32;
+    __align__(16) unsigned char st[S2_WARPS][2][S2_STAGE_BYTES];
+    double slice[S2_WARPS * 32];
+    uint16_t fb[S2_WARPS][FB_CAP];  // chunk-relative point indices
+    uint32_t nfb[S2_WARPS];
+    ScanConst sc;
+};
+static_assert(2 * (sizeof(S2Smem<6>) + 1024) <= 228 * 1024, "two blocks per SM");
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One warp instruction of the cooperative gather: records of lanes 2*JJ and 2*JJ+1 (16 sub-lanes x 16 bytes
+// each). r >= thr with thr = 0 for the 15 copying sub-lanes and INT_MAX for the 16th: one predicate, one wide
+// multiply-add for the source address, one predicated copy.
+template <int JJ>
+__device__ __forceinline__ void gather_pair(int r, const unsigned char* nodes_sub, uint32_t dst0, int thr) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 a;\n\t"
+        "setp.ge.s32 p, %0, %3;\n\t"
+        "mad.wide.u32 a, %0, 256, %1;\n\t"
+        "@p cp.async.cg.shared.global [%2+%4], [a], 16;\n\t}" ::"r"(r),
+        "l"(nodes_sub), "r"(dst0), "r"(thr), "n"(JJ * 2 * TILE_STRIDE)
+        : "memory");
+}
+
+struct Probe {  // what stage B leaves for stage C
+    float4 pt;
+    SlotPair pair;
+    int kx, ky, kz;
+    uint32_t ih;
+};
+
+template <int S2_THREADS>
+__global__ void __launch_bounds__(S2_THREADS, 2) k_residual_stream2(const __grid_constant__ ResidualArgs a) {
+    constexpr int S2_WARPS = S2_THREADS / 32;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    S2Smem<S2_WARPS>* sm = reinterpret_cast<S2Smem<S2_WARPS>*>(s_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const ChunkDesc cd = a.chunks[a.chunk_first + blockIdx.x];
+    if (tid < (int)(sizeof(ScanConst) / sizeof(double)))
+        reinterpret_cast<double*>(&sm->sc)[tid] = reinterpret_cast<const double*>(a.sc + cd.scan)[tid];
+    __syncthreads();
+    const ScanConst& sc = sm->sc;
+    const MapView mv = {a.slots, a.hash_mask, a.nodes};
+    const Globals& g = a.g;
+    const float4* __restrict__ pts = a.pts + cd.start;
+    const uint32_t count = cd.count;
+
+    const int half = lane >> 4, sub = lane & 15;
+    const uint32_t st_base = smem_u32(&sm->st[warp][0][0]);
+    const uint32_t slot_off = (uint32_t)lane * TILE_STRIDE;
+    const uint32_t copy_off = (uint32_t)half * TILE_STRIDE + (uint32_t)sub * 16u;
+    const unsigned char* nodes_sub = reinterpret_cast<const unsigned char*>(mv.nodes) + sub * 16;
+    const int thr = sub < 15 ? 0 : 0x7fffffff;
+
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+    uint32_t nfbw = 0;
+
+    // group i of this warp starts at point (warp + i * S2_WARPS) * 32
+    auto first_of = [&](uint32_t i) { return ((uint32_t)warp + i * (uint32_t)S2_WARPS) * 32u; };
+    auto stage_A = [&](uint32_t i) {  // points
+        const uint32_t p = first_of(i) + (uint32_t)lane;
+        return p < count ? __ldg(pts + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto stage_B = [&](uint32_t i, float4 pt, Probe& pr) {  // key + probe
+        pr.pt = pt;
+        if (first_of(i) + (uint32_t)lane < count) {
+            PointCtx pc;
+            float lx, ly, lz;
+            prepare_point(pt, sc, g, pc, lx, ly, lz);
+            pr.kx = (int)lx; pr.ky = (int)ly; pr.kz = (int)lz;
+            pr.ih = hash_key(pr.kx, pr.ky, pr.kz) & mv.hash_mask;
+            pr.pair = load_pair(mv.slots, pr.ih);
+        }
+    };
+    auto stage_C = [&](uint32_t i, const Probe& pr) {  // root -> gather into stage i & 1 (always commits a group)
+        if (first_of(i) < count) {
+            int root = -1;
+            if (first_of(i) + (uint32_t)lane < count) root = resolve_pair(mv.slots, mv.hash_mask, pr.ih, pr.pair, pr.kx, pr.ky, pr.kz);
+            const uint32_t stage = st_base + (i & 1u) * (uint32_t)S2_STAGE_BYTES;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage + slot_off + S2_SLOT_PT), "f"(pr.pt.x), "f"(pr.pt.y),
+                         "f"(pr.pt.z), "f"(pr.pt.w) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(stage + slot_off + S2_SLOT_ROOT), "r"(root) : "memory");
+            const uint32_t dst0 = stage + copy_off;
+#define LK_G(JJ) gather_pair<JJ>(__shfl_sync(0xffffffffu, root, 2 * JJ + half), nodes_sub, dst0, thr);
+            LK_G(0) LK_G(1) LK_G(2) LK_G(3) LK_G(4) LK_G(5) LK_G(6) LK_G(7)
+            LK_G(8) LK_G(9) LK_G(10) LK_G(11) LK_G(12) LK_G(13) LK_G(14) LK_G(15)
+#undef LK_G
+        }
+        cp_async_commit();
+    };
+
+    const uint32_t n_groups = (count + 31u) >> 5;
+    const uint32_t n_mine = n_groups > (uint32_t)warp ? (n_groups - (uint32_t)warp + S2_WARPS - 1) / S2_WARPS : 0;
+    // prologue
+    Probe pr_c, pr_b;  // pr_c: probed, next to gather; pr_b: being probed
+    pr_c.pair.a = make_int4(0, 0, 0, -1); pr_c.pair.b = pr_c.pair.a; pr_c.kx = pr_c.ky = pr_c.kz = 0; pr_c.ih = 0;
+    pr_c.pt = make_float4(0.f, 0.f, 0.f, 0.f);
+    pr_b = pr_c;
+    float4 pt_a;
+    {
+        stage_B(0, stage_A(0), pr_c);
+        pt_a = stage_A(1);
+        stage_C(0, pr_c);            // gather(0) in flight
+        stage_B(1, pt_a, pr_c);      // probe(1) in flight
+        pt_a = stage_A(2);           // points(2) in flight
+    }
+    for (uint32_t i = 0; i < n_mine; ++i) {
+        stage_C(i + 1, pr_c);             // gather(i+1) -> the other stage (its previous reader finished last round)
+        stage_B(i + 2, pt_a, pr_b);       // probe(i+2)
+        pt_a = stage_A(i + 3);            // points(i+3)
+        cp_async_wait_group<1>();         // gather(i) has landed (this lane's copies) ...
+        __syncwarp();                     // ... and everybody else's
+        {
+            const unsigned char* slot = &sm->st[warp][i & 1u][0] + (size_t)lane * TILE_STRIDE;
+            const int root = *reinterpret_cast<const int*>(slot + S2_SLOT_ROOT);
+            bool fail = false;
+            if (root >= 0) {
+                const float4 pt = *reinterpret_cast<const float4*>(slot + S2_SLOT_PT);
+                PointCtx pc;
+                float lx, ly, lz;
+                prepare_point(pt, sc, g, pc, lx, ly, lz);
+                const uint32_t flags = *reinterpret_cast<const uint32_t*>(slot + 224);
+                Row row;
+                if ((flags & LK_NODE_IS_PLANE) && eval_plane_staged(slot, pc, sc, g, row)) accumulate_row(row, acc);
+                else fail = true;  // not a plane here, or gated out: finished below with the full reference sequence
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, fail);
+            if (fail) sm->fb[warp][nfbw + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(first_of(i) + (uint32_t)lane);
+            nfbw += __popc(m);
+        }
+        __syncwarp();  // the stage is rewritten by the gather issued next round
+        pr_c = pr_b;
+    }
+    cp_async_wait_group<0>();
+    if (lane == 0) sm->nfb[warp] = nfbw;
+    __syncthreads();
+    {
+        uint32_t cnt[S2_WARPS], total = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < S2_WARPS; ++w2) { cnt[w2] = sm->nfb[w2]; total += cnt[w2]; }
+        for (uint32_t e = (uint32_t)tid; e < total; e += S2_THREADS) {
+            uint32_t k = e;
+            int w2 = 0;
+#pragma unroll
+            for (int t = 0; t < S2_WARPS - 1; ++t)
+                if (w2 == t && k >= cnt[t]) { k -= cnt[t]; w2 = t + 1; }
+            Row row;
+            if (point_row(__ldg(pts + sm->fb[w2][k]), sc, mv, g, row, nullptr)) accumulate_row(row, acc);
+        }
+    }
+    const double tot = warp_transpose_sum(acc, lane);
+    sm->slice[warp * 32 + lane] = tot;
+    __syncthreads();
+    if (tid < 32) {
+        double v = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < S2_WARPS; ++w2) v += sm->slice[w2 * 32 + tid];
+        a.partial[(size_t)(a.chunk_first + blockIdx.x) * PARTIAL_STRIDE + tid] = v;
+    }
+}
+
+}  // namespace
+
+void launch_residual_stream2(const ResidualArgs& a, uint32_t n_chunks, cudaStream_t s) {
+    if (n_chunks == 0) return;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_residual_stream2<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S2Smem<6>));
+        cudaFuncSetAttribute(k_residual_stream2<192>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        attr = true;
+    }
+    k_residual_stream2<192><<<n_chunks, 192, sizeof(S2Smem<6>), s>>>(a);
+}
+
+}  // namespace lk
