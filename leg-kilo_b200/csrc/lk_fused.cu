@@ -48,15 +48,16 @@ struct FusedSmem {
 static_assert(sizeof(PredictScratch) <= sizeof(((PassSmem<BLOCK>*)0)->tile), "predict scratch must not reach the mbarriers");
 
 __device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t target) {
+    // the block's partial rows were stored by other threads: bar.sync makes them observed by thread 0, whose
+    // gpu-scope RELEASE reduction (no return value, so no round trip) publishes them cumulatively; the acquire
+    // load that sees the last arrival, followed by bar.sync, orders every thread's reads of the other blocks' rows
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         uint32_t v;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
         } while (v < target);
-        __threadfence();
     }
     __syncthreads();
 }
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
         uint32_t n_last = 0;
         LaneCache lc;
         lc.have = 0;
+        lc.fail = 0;
         const uint32_t n_chunks = in.chunk_end - in.chunk_begin;
         for (int it = 0; it < a.iters; ++it, ++it_global) {
             scan_const_from(&sm->f, &sm->sc);
@@ -177,7 +179,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
             // 4) every block reduces all partial rows in the same fixed order and solves (eskf.cc:91-113)
             block_sum_partials<WARPS>(partial, in.chunk_begin, in.chunk_end, sm->slice, sm->f.acc);
             FT(4 + it_global * 4);
-            const uint32_t n = block_solve_update<BLOCK>(&sm->f, it == a.iters - 1);
+            const uint32_t n = block_solve_update<BLOCK>(&sm->f, it == a.iters - 1,
+                                                         (a.trace && it_global >= 1 && it_global <= 2) ? a.trace + (size_t)(2 * gridDim.x + blockIdx.x) * 64 + (it_global - 1) * 8 : nullptr);
             FT(5 + it_global * 4);
             if (n > 0) {
                 updated = true;

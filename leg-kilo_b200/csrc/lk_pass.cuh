@@ -29,6 +29,7 @@ struct PassSmem {
     uint64_t bar[NTHREADS / 32];
     uint32_t n_fb;
     uint32_t pad;
+    uint32_t wcnt[NTHREADS / 32];  // fallback entries of each warp (its region starts at fb[warp * 32])
 };
 
 struct DebugRows {  // lk_debug_residuals outputs (nullable)
@@ -125,6 +126,7 @@ struct LaneCache {
     double pbx, pby, pbz, pix, piy, piz, r2, range2;
     int kx, ky, kz, nx, ny, nz, root, near;
     int have;  // 0 = nothing cached, 1 = point quantities cached, 2 = + key/root/near/record
+    int fail;  // the point failed at home in the previous iteration (its neighbour record is worth prefetching)
 };
 
 // One pass. `phase` is the warp's mbarrier parity (start at 0, carried between passes).
@@ -211,6 +213,13 @@ __device__ __forceinline__ void block_points_pass(PassSmem<NTHREADS>* ps, uint32
                 const uint32_t in = hash_key(nx, ny, nz) & mv.hash_mask;
                 near = (root >= 0 && differs) ? resolve_pair(mv.slots, mv.hash_mask, in, load_pair(mv.slots, in), nx, ny, nz) : -1;
             }
+            // a point that needed its neighbour voxel last iteration most likely needs it again: pull that record
+            // (two lines) into L1 now, so the fallback round below does not pay an L2 round trip
+            if (lc.have == 2 && lc.fail && near >= 0) {
+                const unsigned char* q = reinterpret_cast<const unsigned char*>(mv.nodes + near);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(q + 128));
+            }
             lc.kx = kx; lc.ky = ky; lc.kz = kz; lc.nx = nx; lc.ny = ny; lc.nz = nz;
             lc.root = root; lc.near = near;
             lc.have = 2;
@@ -243,8 +252,15 @@ __device__ __forceinline__ void block_points_pass(PassSmem<NTHREADS>* ps, uint32
             if (g.max_layer >= 1 && r.child_base >= 0 && cmask)
                 ok = visit_subtree(mv.nodes, r.child_base, cmask, &pc, &sc, &g, &prob, &row);
         }
-        if (!ok && near >= 0) {
-            const uint32_t slot = atomicAdd(&ps->n_fb, 1u);
+        if (CACHED) lc.fail = (!ok && near >= 0) ? 1 : 0;
+    }
+    {
+        // failed points are listed per warp in lane order (no atomics: the order, hence the sums, are reproducible)
+        const bool want = root >= 0 && !ok && near >= 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, want);
+        if (lane == 0) ps->wcnt[warp] = (uint32_t)__popc(m);
+        if (want) {
+            const uint32_t slot = (uint32_t)warp * 32u + (uint32_t)__popc(m & ((1u << lane) - 1u));
             typename PassSmem<NTHREADS>::Fallback& f = ps->fb[slot];
             f.pc[0] = pc.pbx; f.pc[1] = pc.pby; f.pc[2] = pc.pbz; f.pc[3] = pc.pix; f.pc[4] = pc.piy; f.pc[5] = pc.piz;
             f.pc[6] = pc.pwx; f.pc[7] = pc.pwy; f.pc[8] = pc.pwz; f.pc[9] = pc.r2; f.pc[10] = pc.range2;
@@ -266,11 +282,23 @@ __device__ __forceinline__ void block_points_pass(PassSmem<NTHREADS>* ps, uint32
     __syncthreads();
     PT(4);
     // ---- fallback round: the neighbour voxel of the points that failed at home ------------------------
-    const uint32_t n_fb = ps->n_fb;
+    // entry `tid` of the warp-major concatenation of the per-warp lists
+    uint32_t n_fb = 0, fb_slot = 0;
+    {
+        uint32_t k = (uint32_t)tid;
+        bool found = false;
+#pragma unroll
+        for (int w = 0; w < NTHREADS / 32; ++w) {
+            const uint32_t c = ps->wcnt[w];
+            if (!found && k < c) { fb_slot = (uint32_t)w * 32u + k; found = true; }
+            if (!found) k -= c;
+            n_fb += c;
+        }
+    }
     Row row2;
     bool ok2 = false;
     if ((uint32_t)tid < n_fb) {
-        const typename PassSmem<NTHREADS>::Fallback& f = ps->fb[tid];
+        const typename PassSmem<NTHREADS>::Fallback& f = ps->fb[fb_slot];
         PointCtx fc;
         fc.pbx = f.pc[0]; fc.pby = f.pc[1]; fc.pbz = f.pc[2]; fc.pix = f.pc[3]; fc.piy = f.pc[4]; fc.piz = f.pc[5];
         fc.pwx = f.pc[6]; fc.pwy = f.pc[7]; fc.pwz = f.pc[8]; fc.r2 = f.pc[9]; fc.range2 = f.pc[10];

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(BLOCK, (DEBUG || SINGLE) ? 1 : 2) k_residual(c
     uint32_t phase = 0;
     LaneCache lc;
     lc.have = 0;
+    lc.fail = 0;
     for (uint32_t off = 0; off < cd.count; off += BLOCK) {
         const uint32_t n = min((uint32_t)BLOCK, cd.count - off);
         block_points_pass<BLOCK, DEBUG, false>(&rs->pass, phase, a.pts + cd.start + off, n, (size_t)cd.start + off, s_sc,

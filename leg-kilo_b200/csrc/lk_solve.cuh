@@ -62,32 +62,43 @@ __device__ __forceinline__ void block_sum_partials(const double* partial, uint32
 // Warp 0 carries the whole serial chain (A, M = I + A P66, Gauss-Jordan, delta, State (+)) with
 // warp-level synchronisation only; the block joins for the covariance update of the last iteration.
 template <int NTHREADS>
-__device__ __forceinline__ uint32_t block_solve_update(BlockFilter* f, bool last_iter) {
+__device__ __forceinline__ uint32_t block_solve_update(BlockFilter* f, bool last_iter, unsigned long long* clk = nullptr) {
+#define LK_SC(i) do { if (clk && threadIdx.x == 0) clk[i] = (unsigned long long)clock64(); } while (0)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double cnt = f->acc[ACC_CNT];
+    LK_SC(0);
     if (cnt > 0.5) {
         if (warp == 0) {
             // N == 1 adds 1e-4 to S (eskf.cc:100)  <=>  weights scale by R / (R + 1e-4)
             const double scale = (cnt < 1.5) ? f->acc[ACC_SUMR] / (f->acc[ACC_SUMR] + 0.0001) : 1.0;
-            for (int e = lane; e < 36; e += 32) {
-                int i = e / 6, j = e % 6;
-                int r = i < j ? i : j, c = i < j ? j : i;
-                f->A[e] = f->acc[r * 6 - r * (r - 1) / 2 + (c - r)] * scale;
-            }
-            __syncwarp();
+            // columns of [M | b | A], M = I + A P66, one per lane (0..12). Branch-free: every lane forms the six
+            // scaled entries of row i of A from the packed upper triangle (compile-time indices, broadcast reads),
+            // lanes 0..5 run the dot product with their column of P66, the others select.
+            double Pc[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) Pc[k] = f->P[k * 30 + (lane < 6 ? lane : 0)];
+            LK_SC(1);
             double col[6];
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
-                double v = 0.0;
-                if (lane < 6) {  // column `lane` of M = I + A P66
-                    v = (i == lane) ? 1.0 : 0.0;
+                double ar[6];
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) v += f->A[i * 6 + k] * f->P[k * 30 + lane];
-                } else if (lane == 6) v = f->acc[ACC_B + i] * scale;
-                else if (lane < 13) v = f->A[i * 6 + (lane - 7)];
-                col[i] = v;
+                for (int k = 0; k < 6; ++k) {
+                    const int r = i < k ? i : k, c = i < k ? k : i;
+                    ar[k] = f->acc[r * 6 - r * (r - 1) / 2 + (c - r)] * scale;
+                }
+                double m = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) m += ar[k] * Pc[k];
+                double asel = ar[0];
+#pragma unroll
+                for (int t = 1; t < 6; ++t) asel = (lane - 7 == t) ? ar[t] : asel;
+                const double bsel = f->acc[ACC_B + i] * scale;
+                col[i] = lane < 6 ? m : (lane == 6 ? bsel : (lane < 13 ? asel : 0.0));
             }
+            LK_SC(2);
             const bool okl = warp_solve6(col, lane);
+            LK_SC(3);
             double y[6];
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
@@ -99,6 +110,7 @@ __device__ __forceinline__ uint32_t block_solve_update(BlockFilter* f, bool last
 #pragma unroll
                 for (int k = 0; k < 6; ++k) d += f->P[lane * 30 + k] * y[k];
             }
+            LK_SC(4);
             // State::operator+= : Exp(delta_theta) is formed by every lane from the broadcast angles
             const double d0 = __shfl_sync(0xffffffffu, d, 0), d1 = __shfl_sync(0xffffffffu, d, 1),
                          d2 = __shfl_sync(0xffffffffu, d, 2);
@@ -112,8 +124,10 @@ __device__ __forceinline__ uint32_t block_solve_update(BlockFilter* f, bool last
             __syncwarp();
             if (lane < 9) f->x[lane] = rv;
             if (lane >= 3 && lane < 30) f->x[6 + lane] += d;  // delta[3..29] -> x[9..35]
+            LK_SC(5);
         }
         __syncthreads();
+        LK_SC(6);
         if (last_iter) {
             // P <- P - (P6 W) P[0:6,:]   (eskf.cc:112, no symmetrisation)
             for (int e = tid; e < 180; e += NTHREADS) {
@@ -135,6 +149,8 @@ __device__ __forceinline__ uint32_t block_solve_update(BlockFilter* f, bool last
             __syncthreads();
         }
     }
+    LK_SC(7);
+#undef LK_SC
     return (uint32_t)(cnt + 0.5);
 }
 

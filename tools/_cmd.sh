@@ -1,5 +1,5 @@
-timeout 400 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-timeout 400 python bench.py --workload diter_b128 --steps 6 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_diter_b128.json 2>gpurun_out/err_diter.txt; python -c "
-import json
-d=json.load(open('gpurun_out/bench_diter_b128.json')); print('diter_b128 %.3e frac %.3f launch_us %.1f' % (d['value'], d['roofline']['frac'], d['roofline']['avg_launch_us']), d['pose_vs_cpu'], d['clocks'])"
-tail -2 gpurun_out/err_diter.txt
+timeout 200 python tools/trace_fused.py leg_fusion_b1 2>&1 | sed -n 1,5p\;8,9p
+timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_filter.py -x -q -m gpu 2>&1 | tail -3
+timeout 200 python bench.py --steps 2048 --warmup 256 --no-cpu-baseline --no-batched 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('value %.4e us/step %.2f kernel_us %.2f e2e_us %.2f' % (d['value'], d['ms_per_step']*1e3, d['roofline']['avg_launch_us'], d['e2e']['us_per_step']))"

@@ -30,3 +30,7 @@ for scan in (3, 4, 5):
     names = ["load+xform+probe", "tma issue+wait", "read smem", "eval", "sync", "fallback", "accum"]
     print("  pass phases (it1, median over warps / max): " + ", ".join("%s %.2f/%.2f" % (n, np.median(d[:, :, i]), d[:, :, i].max()) for i, n in enumerate(names)))
     print("  fallback entries/block: n/a; pass total med %.2f max %.2f" % (np.median(pt[:, :, 7] - pt[:, :, 0]) / 1e3, (pt[:, :, 7] - pt[:, :, 0]).max() / 1e3))
+    sv = tr[2 * nb * 64: 3 * nb * 64].reshape(nb, 64).astype(np.int64)
+    for it, o in ((1, 0), (2, 8)):
+        dd = np.diff(sv[:, o:o + 8], axis=1) / 1965.0
+        print("  solve it%d (us, median over blocks): " % it + ", ".join("%s %.2f" % (n, np.median(dd[:, k])) for k, n in enumerate(["A", "M cols", "gauss-jordan", "y/W/delta", "exp+state", "syncthreads", "P update"])))
