@@ -184,13 +184,25 @@ int lk_init_process_cov(const lk_eskf_cfg* cfg, double* Q900);
 /* State::State() (eskf.cc:5-16). */
 int lk_state_default(lk_state* x);
 
-/* Pinned host memory for callers that want asynchronous H2D / D2H (cudaHostAlloc / cudaFreeHost). */
+/* Page-locked host memory (cudaHostAlloc / cudaFreeHost). A one-scan lk_scan_update whose `pts` and
+ * `pts_world_out` live in page-locked memory (from here or cudaHostRegister) runs in DIRECT mode: nothing
+ * is staged, the kernel reads the points and stores the world cloud / filter in place. */
 int lk_host_alloc(void** p, size_t bytes);
 int lk_host_free(void* p);
-/* Tuning knobs by name (e.g. "gather_mode": 0 = per-thread vector loads, 1 = bulk-copy staging). */
+/* Tuning / diagnostic knobs by name. Results never depend on them beyond floating-point summation order.
+ *   "fused"       1 (default) one scan per call runs as ONE persistent kernel; 0 = multi-kernel path
+ *   "lane_cache"  1 (default) keep per-lane lookups across the iterations of a bucket (fused kernel)
+ *   "direct_io"   1 (default) allow the direct mode of lk_scan_update; "inline_in" 1 = small inputs ride in
+ *                 the kernel parameter block in direct mode
+ *   "ws"          residual kernel of calls with >= 2 scans: 2 (default) double-buffered stream kernel,
+ *                 1 warp-specialised persistent kernel, 0 single-stage stream kernel
+ *   "coop_launch" 1 = launch the fused kernel through cudaLaunchCooperativeKernel
+ *   "kernel_timing", "trace", "ws_debug", "gather_mode": measurement / debugging aids */
 int lk_set_param(lk_handle h, const char* name, double value);
 
-/* Debug read-back of internal device buffers (what: 0 = per-chunk partial sums, 1 = scan constants). */
+/* Debug read-back (what: 0 = per-chunk partial sums, 1 = scan constants, 2 = %globaltimer trace,
+ * 3 = host-side phase times of lk_scan_update [stage, enqueue, wait+fetch, calls] in ns (reading resets),
+ * 4 = page-locked records of the warp-specialised kernel). */
 int lk_debug_read(lk_handle h, int what, void* dst, size_t bytes);
 
 /* ---- map ------------------------------------------------------------------------------- */
