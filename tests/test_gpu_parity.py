@@ -92,6 +92,45 @@ def test_single_scan_paths_agree_with_oracle(fused):
     globals()[key] = out
 
 
+@pytest.mark.parametrize("ws", [2, 1, 0])
+def test_throughput_family_chunk_edges_and_variants(ws):
+    """Calls with >= 2 scans take the throughput family: 1 920- / 2 048- / 256-point chunks, warps streaming 32-point
+    groups through a software pipeline (ws=2, default), a producer/consumer ring (ws=1) or one stage (ws=0). Scan
+    lengths sit on every edge of that machinery (one point, group and chunk boundaries +-1, several chunks, a warp
+    without work); every variant must reproduce the oracle's residual counts exactly and its state / covariance
+    within tolerance, whatever mixture of lengths shares the call."""
+    cfg, blob, scans = scenes.box_scene(batch=2, lidar=synth.OS64)
+    base = np.concatenate(scans)
+    assert len(base) > 8000
+    sizes = [1, 31, 32, 33, 255, 256, 257, 1919, 1920, 1921, 2047, 2048, 2049, 3839, 3840, 3841, 7777]
+    rs = np.random.default_rng(5)
+    pieces = []
+    for n in sizes:
+        o = int(rs.integers(0, len(base) - n))
+        pieces.append(base[o:o + n].copy())
+    B = len(pieces)
+    pts = np.concatenate(pieces)
+    offs = np.concatenate([[0], np.cumsum([len(s) for s in pieces])]).astype(np.uint32)
+    x0 = abi.default_states(B); P0 = abi.init_cov(B)
+    eng = Engine(cfg)
+    eng.set_param("ws", ws)
+    eng.map_upload(blob)
+    out = eng.scan_update(x0, P0, abi.process_cov_Q(cfg), np.zeros(B, abi.CLOCK_DTYPE), pts, offs, np.zeros(B), iters=2)
+    again = eng.scan_update(x0, P0, abi.process_cov_Q(cfg), np.zeros(B, abi.CLOCK_DTYPE), pts, offs, np.zeros(B), iters=2)
+    np.testing.assert_array_equal(out["P"], again["P"])  # run-to-run bitwise
+    np.testing.assert_array_equal(out["x"].view(np.float64), again["x"].view(np.float64))
+    some = 0
+    for i, s in enumerate(pieces):
+        ro, xo, Po, _ = _oracle_bucket(cfg, blob, s, x0[i:i + 1], P0[i:i + 1], iters=2)
+        assert int(out["n_eff"][i]) == ro["n_eff"], (ws, len(s))
+        if ro["n_eff"] > 0:
+            some += 1
+            assert scenes.rel_state_err(out["x"][i:i + 1], xo, x0[i:i + 1]) < TOL, (ws, len(s))
+            assert scenes.rel_cov_err(out["P"][i], Po) < TOL, (ws, len(s))
+        np.testing.assert_allclose(out["world"][offs[i]:offs[i + 1], :3], ro["world"][:, :3], rtol=0, atol=5e-6)
+    assert some >= len(sizes) - 3
+
+
 @pytest.mark.parametrize("streaming", [False, True])
 def test_direct_io_matches_staged_bitwise(streaming):
     """One scan through lk_scan_update with page-locked caller buffers runs in direct mode (points read in
