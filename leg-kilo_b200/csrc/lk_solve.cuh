@@ -30,21 +30,15 @@ __device__ __forceinline__ void block_sum_partials(const double* partial, uint32
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double acc = 0.0;
     uint32_t c = c0 + warp;
-    for (; c + 7 * NWARPS < c1; c += 8 * NWARPS) {
+    // 16 rows per round (all loads issued before the first add; the adds keep row order, so the result does
+    // not depend on the round size)
+    for (; c < c1; c += 16 * NWARPS) {
         const double* p = partial + (size_t)c * PARTIAL_STRIDE + lane;
-        double v[8];
+        double v[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldcg(p + (size_t)u * NWARPS * PARTIAL_STRIDE);
+        for (int u = 0; u < 16; ++u) v[u] = (c + u * NWARPS < c1) ? __ldcg(p + (size_t)u * NWARPS * PARTIAL_STRIDE) : 0.0;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc += v[u];
-    }
-    {
-        const double* p = partial + (size_t)c * PARTIAL_STRIDE + lane;
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = (c + u * NWARPS < c1) ? __ldcg(p + (size_t)u * NWARPS * PARTIAL_STRIDE) : 0.0;
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < 16; ++u)
             if (c + u * NWARPS < c1) acc += v[u];
     }
     slice[warp * 32 + lane] = acc;

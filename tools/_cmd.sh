@@ -1,6 +1,5 @@
-timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 400 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-timeout 300 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; python -c "
-import json
-d=json.load(open('gpurun_out/bench_default.json')); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['us_per_step'], d['batched']['roofline']['frac'], d['pose_vs_cpu'], d['clocks'])"
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 64 --warmup 8 --no-cpu-baseline --no-e2e --no-batched > gpurun_out/b_under_ncu.log 2>&1; tail -3 gpurun_out/launches.csv | cut -c1-300
+timeout 200 python tools/trace_fused.py leg_fusion_b1 2>&1 | sed -n 1,5p\;8,9p
+timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_filter.py -x -q -m gpu 2>&1 | tail -3
+timeout 200 python bench.py --steps 2048 --warmup 256 --no-cpu-baseline --no-batched 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('value %.4e us/step %.2f kernel_us %.2f e2e_us %.2f' % (d['value'], d['ms_per_step']*1e3, d['roofline']['avg_launch_us'], d['e2e']['us_per_step']))"
