@@ -111,6 +111,7 @@ struct lk_context {
     // throughput family's residual kernel: 2 = double-buffered stream (default), 1 = warp-specialised persistent,
     // 0 = single-stage stream with the in-kernel tail
     int use_ws = 2;
+    int fast_insert = 1;  // update_map: two-launch insert for small buckets, re-projection folded into it
     PinnedBuf h_wdbg;
     bool direct = false, direct_ran = false, inline_ok = false;
     const float4* direct_pts = nullptr;
@@ -327,6 +328,7 @@ int lk_set_param(lk_handle h, const char* name, double value) {
     if (!std::strcmp(name, "kernel_timing")) { h->kernel_timing = (int)value; return LK_OK; }
     if (!std::strcmp(name, "fused")) { h->use_fused = (int)value; return LK_OK; }
     if (!std::strcmp(name, "lane_cache")) { h->lane_cache = (int)value; return LK_OK; }
+    if (!std::strcmp(name, "fast_insert")) { h->fast_insert = (int)value; return LK_OK; }
     if (!std::strcmp(name, "ws_debug")) {
         h->ws_debug = (int)value;
         if (h->ws_debug) {
@@ -686,6 +688,7 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         LK_CUDA(h, h->ins_touched.ensure(mb * 4));
         LK_CUDA(h, h->ins_list.ensure(2 * mb * 4));
         LK_CUDA(h, h->ins_counters.ensure(64));
+        LK_CUDA(h, cudaMemsetAsync(h->ins_counters.p, 0, 64, s));
         if (h->ins_pend_nodes < h->map.node_cap) {
             LK_CUDA(h, h->ins_pend.ensure((size_t)h->map.node_cap * 12));
             LK_CUDA(h, cudaMemsetAsync(h->ins_pend.p, 0, h->ins_pend.cap, s));
@@ -766,6 +769,7 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
     const std::vector<StepInit>& tin = big ? h->h_initsL : h->h_inits;
     const ChunkDesc* d_chunks = big ? h->chunksL.as<ChunkDesc>() : h->chunks.as<ChunkDesc>();
     const StepInit* d_inits = big ? h->stepinitL.as<StepInit>() : h->stepinit.as<StepInit>();
+    uint32_t small_parity = 0;
     uint32_t mi = 0;
     if (mq) {  // the queue is applied BEFORE bucket 0 as well, so the filter is re-loaded here, not in the kernel
         LK_CUDA(h, cudaMemcpyAsync(h->x.as<lk_state>() + first, h->x_in.as<lk_state>() + first, sizeof(lk_state), cudaMemcpyDeviceToDevice, s));
@@ -823,6 +827,16 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
             if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
             if (c1 > c0) { ++h->acc_launches; ++h->acc_residual_launches; }
         }
+        if (update_map && c1 > c0 && h->fast_insert) {
+            // KILO.cc:231 — always, even when no update happened; the insert's first phase also stores the re-projected cloud
+            const StepInit& in = hin[first];
+            h->acc_launches += map_insert_bucket(h->map, h->g, h->pts.as<float4>(), d_chunks, c0, c1 - c0, in.pt_begin,
+                                                 in.pt_end - in.pt_begin, h->sc.as<ScanConst>(), h->step.as<ScanStep>(), h->ins_pts.p,
+                                                 h->ins_root.as<int>(), h->ins_pend.as<int>(), h->ins_touched.as<uint32_t>(),
+                                                 h->ins_counters.as<uint32_t>(), h->ins_list.as<uint32_t>(), s,
+                                                 h->world.as<float4>(), &small_parity);
+            continue;
+        }
         ReprojectArgs rp;
         rp.pts = h->pts.as<float4>();
         rp.world = h->world.as<float4>();
@@ -835,11 +849,10 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         if (c1 > c0) ++h->acc_launches;
         if (update_map && c1 > c0) {  // KILO.cc:231 — always, even when no update happened
             const StepInit& in = hin[first];
-            map_insert_bucket(h->map, h->g, h->pts.as<float4>(), d_chunks, c0, c1 - c0, in.pt_begin,
-                              in.pt_end - in.pt_begin, h->sc.as<ScanConst>(), h->step.as<ScanStep>(), h->ins_pts.p,
-                              h->ins_root.as<int>(), h->ins_pend.as<int>(), h->ins_touched.as<uint32_t>(),
-                              h->ins_counters.as<uint32_t>(), h->ins_list.as<uint32_t>(), s);
-            h->acc_launches += 4;
+            h->acc_launches += map_insert_bucket(h->map, h->g, h->pts.as<float4>(), d_chunks, c0, c1 - c0, in.pt_begin,
+                                                 in.pt_end - in.pt_begin, h->sc.as<ScanConst>(), h->step.as<ScanStep>(), h->ins_pts.p,
+                                                 h->ins_root.as<int>(), h->ins_pend.as<int>(), h->ins_touched.as<uint32_t>(),
+                                                 h->ins_counters.as<uint32_t>(), h->ins_list.as<uint32_t>(), s);
         }
     }
     LK_CUDA(h, cudaGetLastError());

@@ -10,6 +10,9 @@
 //   P3  per point: drop the point index into its root's slice;
 //   P4  one warp per touched root: order the slice by point index (= the reference's insertion
 //       order) and run UpdateOctoTree sequentially on it, with the warp-cooperative plane refit.
+// Small buckets (the 2 ms buckets of streaming mode: a few hundred points) skip P2 / P3 and the sort: the
+// warp of a touched root simply scans the bucket's root-per-point array in index order (P4S), and P1 also
+// stores the re-projected world point (KILO.cc:216-224), so a bucket costs two launches instead of six.
 #include "lk_kernels.h"
 #include "lk_mapdev.h"
 #include "lk_octree.cuh"
@@ -34,6 +37,8 @@ struct InsertArgs {
     uint32_t* counters;  // [0] n_touched  [1] list bump
     uint32_t* list;      // [2 * bucket points]  (second half = sort scratch)
     uint32_t n_pts;
+    float4* world;       // non-null: P1 also writes cloud_down_world (x, y, z, intensity 0 | 255)
+    uint32_t cslot;      // which of the two n_touched counters this bucket uses (small-bucket path)
 };
 
 __device__ __forceinline__ int hash_find_or_create(MapDev& md, const Globals& g, int kx, int ky, int kz) {
@@ -127,6 +132,12 @@ __global__ void __launch_bounds__(256) k_insert_p1(const __grid_constant__ Inser
         p.pad = 0.0;
         const uint32_t li = cd.start + i - a.pt_base;
         a.ipts[li] = p;
+        if (a.world) {
+            float4 o;
+            o.x = (float)p.pw[0]; o.y = (float)p.pw[1]; o.z = (float)p.pw[2];
+            o.w = a.step[cd.scan].updated ? 255.0f : 0.0f;
+            a.world[cd.start + i] = o;
+        }
         // voxelKeyFloor(point_w, (double)(float)voxel_size)  (voxel_map.cc:337,343)
         const double vs = (double)g.voxel_f;
         const int kx = (int)floor(p.pw[0] / vs), ky = (int)floor(p.pw[1] / vs), kz = (int)floor(p.pw[2] / vs);
@@ -134,7 +145,7 @@ __global__ void __launch_bounds__(256) k_insert_p1(const __grid_constant__ Inser
         a.iroot[li] = root;
         if (root >= 0) {
             const int c = atomicAdd(&a.pend[root * 3], 1);
-            if (c == 0) a.touched[atomicAdd(&a.counters[0], 1u)] = (uint32_t)root;
+            if (c == 0) a.touched[atomicAdd(&a.counters[a.cslot], 1u)] = (uint32_t)root;
         }
     }
 }
@@ -192,13 +203,49 @@ __global__ void __launch_bounds__(128) k_insert_p4(const __grid_constant__ Inser
     if (lane == 0) a.pend[root * 3] = 0;
 }
 
+// P4S — small buckets: one warp per touched root walks the bucket's root-per-point array in index order
+// (= the order UpdateVoxelMap walks input_points) and inserts its own points; no slices, no sort.
+__global__ void __launch_bounds__(128) k_insert_p4_scan(const __grid_constant__ InsertArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpTile* tiles = reinterpret_cast<WarpTile*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpTile* wt = tiles + warp;
+    if (lane == 0) {
+        mbar_init(&wt->bar, 1);
+        wt->phase = 0;
+        mbar_init_fence();
+    }
+    __syncwarp();
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.counters[a.cslot ^ 1u] = 0;  // the next bucket's counter
+    const uint32_t t = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (t >= a.counters[a.cslot]) return;
+    const uint32_t root = a.touched[t];
+    const int cnt = a.pend[root * 3];
+    MapDev md = a.md;
+    int done = 0;
+    for (uint32_t base = 0; base < a.n_pts && done < cnt; base += 32) {
+        const uint32_t j = base + (uint32_t)lane;
+        const int r = j < a.n_pts ? a.iroot[j] : -1;
+        uint32_t m = __ballot_sync(0xffffffffu, r == (int)root);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const DevPoint p = a.ipts[base + (uint32_t)b];
+            warp_update_octo_tree(md, a.g, wt, root, p, lane);
+            ++done;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) a.pend[root * 3] = 0;
+}
+
 }  // namespace
 
 // Scratch owned by the caller (lk_api): sized for the largest bucket.
 int map_insert_bucket(MapDevHost& mh, const Globals& g, const float4* pts, const ChunkDesc* chunks, uint32_t chunk_first,
                       uint32_t n_chunks, uint32_t pt_begin, uint32_t n_pts, const ScanConst* sc, const ScanStep* step,
                       void* ipts, int* iroot, int* pend, uint32_t* touched, uint32_t* counters, uint32_t* list,
-                      cudaStream_t s) {
+                      cudaStream_t s, float4* world, uint32_t* small_parity) {
     if (!n_pts || !n_chunks) return LK_OK;
     InsertArgs a;
     a.md = mh.dev();
@@ -216,13 +263,25 @@ int map_insert_bucket(MapDevHost& mh, const Globals& g, const float4* pts, const
     a.counters = counters;
     a.list = list;
     a.n_pts = n_pts;
+    a.world = world;
+    a.cslot = 0;
+    const int wpb = 4;
+    if (small_parity && n_pts <= 4096u) {
+        // counters[2 + parity] is this bucket's n_touched; P4S zeroes the other one for the next bucket (the caller
+        // zeroed both before the first bucket of the scan)
+        a.counters = counters + 2;
+        a.cslot = *small_parity;
+        *small_parity ^= 1u;
+        k_insert_p1<<<n_chunks, 256, 0, s>>>(a);
+        k_insert_p4_scan<<<(n_pts + wpb - 1) / wpb, wpb * 32, wpb * sizeof(WarpTile), s>>>(a);
+        return 2;
+    }
     cudaMemsetAsync(counters, 0, 8, s);
     k_insert_p1<<<n_chunks, 256, 0, s>>>(a);
     k_insert_p2<<<(n_pts + 255) / 256, 256, 0, s>>>(a);
     k_insert_p3<<<(n_pts + 255) / 256, 256, 0, s>>>(a);
-    const int wpb = 4;
     k_insert_p4<<<(n_pts + wpb - 1) / wpb, wpb * 32, wpb * sizeof(WarpTile), s>>>(a);
-    return LK_OK;
+    return 5;
 }
 
 size_t insert_point_bytes() { return sizeof(DevPoint); }

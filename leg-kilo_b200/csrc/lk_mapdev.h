@@ -39,11 +39,14 @@ class MapDevHost {
 // lk_mapbuild.cu
 int map_build_device(MapDevHost& mh, const Globals& g, const float* d_xyz_world, const float* d_xyz_body, uint32_t n,
                      const double* rot, const double* rot_cov, const double* pos_cov, cudaStream_t s, std::string& err);
-// lk_insert.cu — UpdateVoxelMap for one bucket (scratch buffers owned by the caller)
+// lk_insert.cu — UpdateVoxelMap for one bucket (scratch buffers owned by the caller). Returns the number of
+// launches (0 = nothing to do). world != null: the bucket's re-projected cloud is written too (the caller then
+// skips its own re-projection kernel). small_parity != null enables the two-launch path for buckets of up to
+// 4 096 points; the caller zeroes counters[2..3] and *small_parity before the first bucket of a scan.
 int map_insert_bucket(MapDevHost& mh, const Globals& g, const float4* pts, const ChunkDesc* chunks, uint32_t chunk_first,
                       uint32_t n_chunks, uint32_t pt_begin, uint32_t n_pts, const ScanConst* sc, const ScanStep* step,
                       void* ipts, int* iroot, int* pend, uint32_t* touched, uint32_t* counters, uint32_t* list,
-                      cudaStream_t s);
+                      cudaStream_t s, float4* world = nullptr, uint32_t* small_parity = nullptr);
 size_t insert_point_bytes();
 // lk_mapio.cu
 int map_upload_blob(MapDevHost& mh, const Globals& g, const void* blob, size_t bytes, cudaStream_t s, std::string& err);

@@ -1,5 +1,11 @@
-timeout 200 python tools/trace_fused.py leg_fusion_b1 2>&1 | sed -n 1,5p\;8,9p
-timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_filter.py -x -q -m gpu 2>&1 | tail -3
-timeout 200 python bench.py --steps 2048 --warmup 256 --no-cpu-baseline --no-batched 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('value %.4e us/step %.2f kernel_us %.2f e2e_us %.2f' % (d['value'], d['ms_per_step']*1e3, d['roofline']['avg_launch_us'], d['e2e']['us_per_step']))"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 1500 --csv --log-file gpurun_out/launches_stream.csv python bench.py --workload nclt_stream > gpurun_out/b_stream_ncu.log 2>&1
+python - <<'PY'
+import csv, collections
+rows=[r for r in csv.reader(open('gpurun_out/launches_stream.csv')) if len(r)>10 and r[0].isdigit()]
+t=collections.defaultdict(float); n=collections.Counter()
+for r in rows:
+    k=r[4].split('(')[0].replace('lk::<unnamed>::','')[:50]; t[k]+=float(r[-1])/1e3; n[k]+=1
+tot=sum(t.values())
+for k,v in sorted(t.items(), key=lambda kv:-kv[1])[:14]: print('%-50s n=%5d total %8.1f us avg %6.2f us share %.1f%%' % (k, n[k], v, v/n[k], 100*v/tot))
+print('launches', len(rows), 'total us', tot)
+PY
