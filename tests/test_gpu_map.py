@@ -65,7 +65,7 @@ def test_map_upload_download_roundtrip():
     assert st["planes"] == 576
 
 
-def _stream_case(streaming, iters=1, stream0=700, empty_map=False, n_scans=2):
+def _stream_case(streaming, iters=1, stream0=700, empty_map=False, n_scans=2, fast_insert=1, check_world=False):
     import test_gpu_parity as tp
     cfg, blob, scans = scenes.box_scene(batch=2, streaming=streaming, stream0=stream0)
     x0 = tp._moving_state() if streaming else abi.default_states(1)
@@ -73,6 +73,7 @@ def _stream_case(streaming, iters=1, stream0=700, empty_map=False, n_scans=2):
     clk = np.zeros(1, abi.CLOCK_DTYPE); clk["last_predict_time"] = 9.99; clk["last_update_time"] = 9.985
     o = lko.Oracle(cfg)
     eng = Engine(cfg)
+    eng.set_param("fast_insert", fast_insert)
     if not empty_map:
         o.map_import(blob)
         eng.map_upload(blob)
@@ -89,6 +90,9 @@ def _stream_case(streaming, iters=1, stream0=700, empty_map=False, n_scans=2):
         assert int(out["n_eff"][0]) == ro["n_eff"]
         assert scenes.rel_state_err(out["x"], xo, x0) < 1e-5
         assert scenes.rel_cov_err(out["P"][0], Po) < 1e-5
+        if check_world:  # the re-projected cloud comes out of the insert's first phase on the fast path
+            np.testing.assert_allclose(out["world"][:, :3], ro["world"][:, :3], rtol=0, atol=5e-6)
+            np.testing.assert_array_equal(out["world"][:, 3], ro["world"][:, 3])
         xg, Pg, cg = out["x"], out["P"], out["clk"]
         t0 += 0.1
     # the device state differs from the oracle's by ~1e-11 relative, so do the inserted points
@@ -98,15 +102,17 @@ def _stream_case(streaming, iters=1, stream0=700, empty_map=False, n_scans=2):
 
 def test_update_map_scan_at_once():
     """One bucket per scan: update, re-project, then UpdateVoxelMap of all ~28 k points (KILO.cc:215-231)."""
-    st = _stream_case(streaming=False)
+    st = _stream_case(streaming=False, check_world=True)
     assert st["planes"] > 3000
 
 
+@pytest.mark.parametrize("fast_insert", [1, 0])
 @pytest.mark.parametrize("iters", [1, 2])
-def test_update_map_streaming(iters):
+def test_update_map_streaming(iters, fast_insert):
     """~50 buckets per scan, map mutated between buckets (refits every 6th insertion per leaf, freezes
-    at 50 points, new roots / octants on demand) — the full reference loop on the device."""
-    st = _stream_case(streaming=True, iters=iters)
+    at 50 points, new roots / octants on demand) — the full reference loop on the device, through both insert
+    paths (two launches per small bucket / the general slice-and-sort path)."""
+    st = _stream_case(streaming=True, iters=iters, fast_insert=fast_insert, check_world=True)
     assert st["planes"] > 3000
 
 
