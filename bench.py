@@ -44,12 +44,17 @@ WORKLOADS = {
 
 
 def ncu_traffic(kernel):
+    """(dram bytes per launch, note) of the kernel's committed `ncu --set full` capture, or (None, None)."""
     p = os.path.join(ROOT, "profiles", "r1_traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get(kernel)
+            e = json.load(f).get(kernel)
     except (OSError, ValueError):
-        return None
+        e = None
+    if not e:
+        return None, None
+    return float(e["dram_bytes_per_launch"]), "ncu capture on: %s; algorithmic bytes of that launch %.3g" % (
+        e["workload"], e["algorithmic_bytes_per_launch"])
 
 
 def measured_peaks():
@@ -368,8 +373,9 @@ def main():
     alg_bytes_per_launch = ALG_BYTES_PER_POINT_ITER * (work / r_launches)
     achieved = alg_bytes_per_launch / (res_ms * 1e-3) / 1e9 if res_ms > 0 else 0.0
     fused = (B == 1 and args.fused != 0)
+    traffic, traffic_note = ncu_traffic("k_scan_fused" if fused else "k_residual_stream2")
     roofline = dict(bound="hbm", kernel="k_scan_fused (whole scan: 3 x [residual+reduce+solve] + re-projection)" if fused else ("k_residual_stream2 (+ k_scan_tail, the per-scan solve)" if B >= 2 else "k_residual"), achieved=achieved, peak=hbm_peak, unit="GB/s",
-                    frac=achieved / hbm_peak, traffic=ncu_traffic("k_scan_fused" if fused else "k_residual_stream2"),
+                    frac=achieved / hbm_peak, traffic=traffic, traffic_note=traffic_note,
                     peak_source=peak_src,
                     alg_bytes_per_launch=alg_bytes_per_launch, avg_launch_us=res_ms * 1e3,
                     share_of_step=tm["residual_ms"] / tm["total_ms"] if tm["total_ms"] > 0 else None)

@@ -154,12 +154,6 @@ int fail(lk_handle h, int code, const std::string& msg) {
         }                                                                                             \
     } while (0)
 
-uint64_t next_pow2(uint64_t v) {
-    uint64_t p = 1;
-    while (p < v) p <<= 1;
-    return p;
-}
-
 void fill_globals(lk_context* c, const double* extR, const double* extT) {
     Globals& g = c->g;
     for (int i = 0; i < 9; ++i) g.Re[i] = extR[i];
