@@ -129,6 +129,25 @@ def test_throughput_family_chunk_edges_and_variants(ws):
             assert scenes.rel_cov_err(out["P"][i], Po) < TOL, (ws, len(s))
         np.testing.assert_allclose(out["world"][offs[i]:offs[i + 1], :3], ro["world"][:, :3], rtol=0, atol=5e-6)
     assert some >= len(sizes) - 3
+    # many small scans: more chunks than SMs, so the persistent variant walks several chunks per block (stage ring
+    # re-used across chunk and scan boundaries) and the others run several waves
+    sizes2 = [int(v) for v in rs.integers(260, 700, size=220)]
+    pieces2 = []
+    for n in sizes2:
+        o = int(rs.integers(0, len(base) - n))
+        pieces2.append(base[o:o + n].copy())
+    B2 = len(pieces2)
+    pts2 = np.concatenate(pieces2)
+    offs2 = np.concatenate([[0], np.cumsum(sizes2)]).astype(np.uint32)
+    x2 = abi.default_states(B2); P2 = abi.init_cov(B2)
+    out2 = eng.scan_update(x2, P2, abi.process_cov_Q(cfg), np.zeros(B2, abi.CLOCK_DTYPE), pts2, offs2, np.zeros(B2), iters=2,
+                           want_world=False)
+    for i in range(0, B2, 7):
+        ro, xo, Po, _ = _oracle_bucket(cfg, blob, pieces2[i], x2[i:i + 1], P2[i:i + 1], iters=2)
+        assert int(out2["n_eff"][i]) == ro["n_eff"], (ws, i)
+        if ro["n_eff"] > 0:
+            assert scenes.rel_state_err(out2["x"][i:i + 1], xo, x2[i:i + 1]) < TOL, (ws, i)
+            assert scenes.rel_cov_err(out2["P"][i], Po) < TOL, (ws, i)
 
 
 @pytest.mark.parametrize("streaming", [False, True])
