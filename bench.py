@@ -152,8 +152,12 @@ def cpu_reference_run(wl, w, scan_ids, nthreads, gain_information=True):
     for r in rooms:
         cx, cy = scene.rooms[r]
         keep |= (np.abs(pw[:, 0] - cx) < scene.W + 2.25) & (np.abs(pw[:, 1] - cy) < scene.W + 2.25)
-    o = lko.Oracle(cfg)
-    o.build_voxel_map(pw[keep], pb[keep])
+    cache = wl.setdefault("_oracle_cache", {})
+    o = cache.get(tuple(rooms))
+    if o is None:  # the map of these rooms is built once (outside every timed region) and only read afterwards
+        o = lko.Oracle(cfg)
+        o.build_voxel_map(pw[keep], pb[keep])
+        cache[tuple(rooms)] = o
     o.set_filter(None, None, abi.process_cov_Q(cfg), None)
     n = len(scan_ids)
     pts = np.concatenate([wl["scans"][i] for i in scan_ids])
@@ -276,28 +280,40 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        wl = build_workload(w, 0, max(args.cpu_scans, 4))
-        wl["rank"] = 0
         ncores = os.cpu_count() or 1
-        per_step = max(ncores, 1)  # one scan per host thread per step
-        ids = list(range(min(per_step, len(wl["scans"]))))
+        # One scan per host thread, every thread busy: the reference's per-scan loop is serial (KILO.cc:122), so the only
+        # way it can use the box is independent scans side by side. The sample is ncores scans taken room by room (the
+        # oracle then builds the map of those rooms only, outside the timed region).
+        ring_n = min(512, max(64, 4 * ncores))
+        wl = build_workload(w, 0, ring_n)
+        wl["rank"] = 0
+        n_rooms = len(wl["scene"].rooms)
+        order = sorted(range(ring_n), key=lambda i: ((i * 7) % n_rooms, i))
+        ids = order[:min(ncores, ring_n)]
+        nthreads = len(ids)
         for _ in range(max(1, min(W, 2))):
-            cpu_reference_run(wl, w, ids, ncores)
+            cpu_reference_run(wl, w, ids, nthreads)
         steps = max(1, min(K, 3))
         tot_s, tot_pts = 0.0, 0
         for _ in range(steps):
-            sec, _, _, _, npts = cpu_reference_run(wl, w, ids, ncores)
+            sec, _, _, _, npts = cpu_reference_run(wl, w, ids, nthreads)
             tot_s += sec
             tot_pts += npts * w["iters"]
         val = tot_pts / tot_s
+        # the same loop on ONE scan with one thread: what a single scan (the step of the CUDA arm) gets from this CPU
+        sec1, _, _, _, npts1 = cpu_reference_run(wl, w, ids[:2], 1)
+        one_thread = npts1 * w["iters"] / sec1
         line = dict(metric="LiDAR point-iterations/sec through the ESKF point-to-plane update", value=val,
                     unit="point-iterations/s", impl="reference", n_gpus=args.gpus, steps=steps, warmup=min(W, 2),
                     ms_per_step=1e3 * tot_s / steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f64", data="synthetic",
                     config=dict(workload=args.workload, baseline_config=w["baseline_config"], iters=w["iters"],
-                                note="CPU restatement of the reference path (oracle/, information-form gain), one scan per host thread"),
-                    cpu_baseline=dict(value=val, unit="point-iterations/s", cores=ncores, kind="port",
-                                      sample=f"{len(ids)} scans x ~{len(wl['scans'][0])} pts x {w['iters']} iters per step, {steps} steps"),
+                                note="CPU restatement of the reference path (oracle/, information-form gain), one scan per host thread, "
+                                     "%d scans side by side" % nthreads),
+                    cpu_baseline=dict(value=val, unit="point-iterations/s", cores=nthreads, kind="port",
+                                      sample=f"{len(ids)} scans x ~{len(wl['scans'][0])} pts x {w['iters']} iters per step, {steps} steps, "
+                                             f"{nthreads} threads of {ncores} hardware threads",
+                                      single_scan_one_thread=one_thread),
                     e2e=dict(value=val, unit="point-iterations/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return 0
