@@ -354,6 +354,12 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    fused = (B == 1 and args.fused != 0)
+    if fused:
+        # one kernel per step: its average duration over the timed region is region / launches. Per-launch events
+        # would sit between consecutive launches and defeat their overlap (programmatic dependent launch).
+        eng.set_param("kernel_timing", 0)
+
     # warm-up (also warms the ring once when W >= groups)
     for i in range(W):
         eng.run_range((i % groups) * B, B, iters=w["iters"])
@@ -385,20 +391,23 @@ def main():
 
     # roofline of the dominant kernel (k_residual): algorithmic bytes / its own event-timed duration
     r_launches = max(tm["residual_launches"], 1)
-    res_ms = tm["residual_ms"] / r_launches
+    res_total_ms = tm["total_ms"] if fused else tm["residual_ms"]
+    res_ms = res_total_ms / r_launches
     alg_bytes_per_launch = ALG_BYTES_PER_POINT_ITER * (work / r_launches)
     achieved = alg_bytes_per_launch / (res_ms * 1e-3) / 1e9 if res_ms > 0 else 0.0
-    fused = (B == 1 and args.fused != 0)
     traffic, traffic_note = ncu_traffic("k_scan_fused" if fused else "k_residual_stream2")
     roofline = dict(bound="hbm", kernel="k_scan_fused (whole scan: 3 x [residual+reduce+solve] + re-projection)" if fused else ("k_residual_stream2 (+ k_scan_tail, the per-scan solve)" if B >= 2 else "k_residual"), achieved=achieved, peak=hbm_peak, unit="GB/s",
                     frac=achieved / hbm_peak, traffic=traffic, traffic_note=traffic_note,
                     peak_source=peak_src,
                     alg_bytes_per_launch=alg_bytes_per_launch, avg_launch_us=res_ms * 1e3,
-                    share_of_step=tm["residual_ms"] / tm["total_ms"] if tm["total_ms"] > 0 else None)
+                    share_of_step=res_total_ms / tm["total_ms"] if tm["total_ms"] > 0 else None,
+                    timing="CUDA events around the timed region / launches in it (the step is this one kernel)" if fused
+                    else "CUDA events around every launch of the kernel")
 
     # the same ring as ONE batch (all scans in one launch sequence): the throughput mode of the same path
     batched = None
     if B == 1 and nsc >= 64 and not args.no_batched:
+        eng.set_param("kernel_timing", 1)
         for _ in range(2):
             eng.run_range(0, nsc, iters=w["iters"])
         eng.sync()

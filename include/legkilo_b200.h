@@ -194,15 +194,15 @@ int lk_host_free(void* p);
  *   "lane_cache"  1 (default) keep per-lane lookups across the iterations of a bucket (fused kernel)
  *   "direct_io"   1 (default) allow the direct mode of lk_scan_update; "inline_in" 1 = small inputs ride in
  *                 the kernel parameter block in direct mode
- *   "ws"          residual kernel of calls with >= 2 scans: 2 (default) double-buffered stream kernel,
- *                 1 warp-specialised persistent kernel, 0 single-stage stream kernel
- *   "coop_launch" 1 = launch the fused kernel through cudaLaunchCooperativeKernel
- *   "kernel_timing", "trace", "ws_debug", "gather_mode": measurement / debugging aids */
+ *   "pdl"         1 (default) back-to-back fused launches of one stream use programmatic dependent launch: the
+ *                 next scan's blocks run their prologue while the previous scan's last blocks drain
+ *   "coop_launch" 1 = launch the fused kernel through cudaLaunchCooperativeKernel (co-residency checked by the
+ *                 driver; for devices shared with OTHER processes, see INTEGRATION.md "Sharing a device")
+ *   "kernel_timing", "trace", "gather_mode": measurement / debugging aids */
 int lk_set_param(lk_handle h, const char* name, double value);
 
 /* Debug read-back (what: 0 = per-chunk partial sums, 1 = scan constants, 2 = %globaltimer trace,
- * 3 = host-side phase times of lk_scan_update [stage, enqueue, wait+fetch, calls] in ns (reading resets),
- * 4 = page-locked records of the warp-specialised kernel). */
+ * 3 = host-side phase times of lk_scan_update [stage, enqueue, wait+fetch, calls] in ns (reading resets)). */
 int lk_debug_read(lk_handle h, int what, void* dst, size_t bytes);
 
 /* ---- map ------------------------------------------------------------------------------- */

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <chrono>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -103,16 +104,15 @@ struct lk_context {
     int trace_on = 0;
     int lane_cache = 1;
     int use_fused = 1;      // batch-of-one runs go through the persistent per-scan kernel
-    int fused_parity = 0;
+    FusedInline inl;         // parameter-block image of the small inputs (direct mode)
+    DevBuf ll;               // flagged rows of the fused kernel's all-reduce (lk_llsync.cuh), zero-filled once
+    uint32_t ll_epoch = 1;   // next unused tag (0 = the fill value, never used)
+    bool prev_fused = false;  // the last operation enqueued on `stream` was a fused launch (PDL is only used then)
     uint32_t fused_launches = 0;
     // direct mode of lk_scan_update (one scan, page-locked caller buffers): the kernel reads the points and
     // writes the world cloud / the filter in place, the small inputs ride in the kernel's parameter block
-    int direct_io = 1, inline_in = 1, coop_launch = 0, n_sms = 148, ws_debug = 0;
-    // throughput family's residual kernel: 2 = double-buffered stream (default), 1 = warp-specialised persistent,
-    // 0 = single-stage stream with the in-kernel tail
-    int use_ws = 2;
+    int direct_io = 1, inline_in = 1, coop_launch = 0, pdl = 1, n_sms = 148;
     int fast_insert = 1;  // update_map: two-launch insert for small buckets, re-projection folded into it
-    PinnedBuf h_wdbg;
     bool direct = false, direct_ran = false, inline_ok = false;
     const float4* direct_pts = nullptr;
     float4* direct_world = nullptr;
@@ -142,6 +142,17 @@ int fail(lk_handle h, int code, const std::string& msg) {
     if (h) h->err = msg;
     else g_create_error = msg;
     return code;
+}
+
+// One per device: the stream of the most recent fused launch of this process (see run_range_impl).
+struct FusedGate {
+    std::mutex m;
+    cudaStream_t last = nullptr;
+    cudaEvent_t ev = nullptr;
+};
+FusedGate& fused_gate(int device) {
+    static FusedGate gates[64];
+    return gates[(device >= 0 && device < 64) ? device : 0];
 }
 
 #define LK_CUDA(h, expr)                                                                              \
@@ -180,13 +191,14 @@ void fill_globals(lk_context* c, const double* extR, const double* extT) {
 
 // Chunking is a function of the bucket and of the kernel family alone, so results are bitwise independent
 // of how a batch is sharded across GPUs (SURVEY §4 multi-GPU invariant).
-//   latency family (one scan per call): buckets up to 64 Ki points use one point per thread (256-point
-//     chunks, one per SM); larger ones 2 048-point chunks streamed by warps;
-//   throughput family (>= 2 scans per call): 2 048-point chunks as soon as a bucket exceeds one of them —
-//     every warp then streams 8 groups and the per-chunk reduce / ticket is amortised.
-uint32_t chunk_size_for(uint32_t n, bool throughput, uint32_t big = 2048u) {
+//   latency family (one scan per call): buckets up to 148 x 256 points use one point per thread (256-point
+//     chunks, one per SM: the fused kernel); larger ones the throughput family's chunks;
+//   throughput family (>= 2 scans per call): 1 920-point chunks as soon as a bucket exceeds 2 048 points —
+//     every warp then streams 10 groups and the per-chunk reduce is amortised.
+constexpr uint32_t LATENCY_MAX_BUCKET = 148u * 256u;  // one 256-point chunk per SM of a B200: the fused kernel's reach
+uint32_t chunk_size_for(uint32_t n, bool throughput, uint32_t big = 1920u) {
     if (throughput) return n <= 2048u ? 256u : big;
-    return n <= 65536u ? 256u : 2048u;
+    return n <= LATENCY_MAX_BUCKET ? 256u : big;
 }
 
 cudaEvent_t kev_get(lk_context* c, size_t i) {
@@ -215,7 +227,6 @@ ResidualArgs residual_args(lk_context* c, const ChunkDesc* chunks) {
     a.clk = c->clk.as<lk_stream_clock>();
     a.n_eff = c->n_eff.as<uint32_t>();
     a.trace = c->trace_on ? c->trace.as<unsigned long long>() : nullptr;
-    a.wdbg = c->ws_debug ? (unsigned long long*)c->h_wdbg.p : nullptr;
     a.g = c->g;
     return a;
 }
@@ -265,11 +276,17 @@ int lk_create(const lk_eskf_cfg* eskf_cfg, const lk_map_cfg* map_cfg, const doub
 int lk_destroy(lk_handle h) {
     if (!h) return LK_OK;
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     cudaStreamSynchronize(h->stream);
+    {
+        FusedGate& gate = fused_gate(h->device);
+        std::lock_guard<std::mutex> lock(gate.m);
+        if (gate.last == h->stream) gate.last = nullptr;
+    }
     h->map.release();
     DevBuf* bufs[] = {&h->pts, &h->world,
                       &h->sc, &h->step, &h->partial, &h->ticket, &h->small_in, &h->small_out, &h->fx, &h->fP, &h->fQ, &h->fclk, &h->dbg_ok, &h->dbg_h, &h->dbg_z, &h->dbg_R,
-                      &h->dbg_key, &h->tmp, &h->trace, &h->bar, &h->ins_pts, &h->ins_root, &h->ins_pend, &h->ins_touched,
+                      &h->dbg_key, &h->tmp, &h->trace, &h->ll, &h->Qc, &h->ins_pts, &h->ins_root, &h->ins_pend, &h->ins_touched,
                       &h->ins_counters, &h->ins_list};
     for (DevBuf* b : bufs) b->release();
     h->h_small_in.release();
@@ -323,22 +340,15 @@ int lk_set_param(lk_handle h, const char* name, double value) {
     if (!std::strcmp(name, "fused")) { h->use_fused = (int)value; return LK_OK; }
     if (!std::strcmp(name, "lane_cache")) { h->lane_cache = (int)value; return LK_OK; }
     if (!std::strcmp(name, "fast_insert")) { h->fast_insert = (int)value; return LK_OK; }
-    if (!std::strcmp(name, "ws_debug")) {
-        h->ws_debug = (int)value;
-        if (h->ws_debug) {
-            if (h->h_wdbg.ensure(256 * 16 * 8 * 8) != cudaSuccess) return LK_ERR_OUT_OF_MEMORY;
-            std::memset(h->h_wdbg.p, 0, 256 * 16 * 8 * 8);
-        }
-        return LK_OK;
-    }
-    if (!std::strcmp(name, "ws")) { h->use_ws = (int)value; return LK_OK; }
     if (!std::strcmp(name, "coop_launch")) { h->coop_launch = (int)value; return LK_OK; }
+    if (!std::strcmp(name, "pdl")) { h->pdl = (int)value; return LK_OK; }
     if (!std::strcmp(name, "direct_io")) { h->direct_io = (int)value; return LK_OK; }
     if (!std::strcmp(name, "inline_in")) { h->inline_in = (int)value; return LK_OK; }
     if (!std::strcmp(name, "trace")) {
         h->trace_on = (int)value;
         if (h->trace_on) {
             cudaSetDevice(h->device);
+            h->prev_fused = false;
             LK_CUDA(h, h->trace.ensure((size_t)(1 << 16) * 8 * 8));
             LK_CUDA(h, cudaMemset(h->trace.p, 0, (size_t)(1 << 16) * 8 * 8));
         }
@@ -350,17 +360,13 @@ int lk_set_param(lk_handle h, const char* name, double value) {
 // Debug read-back of internal device buffers: what = 0 partial sums, 1 scan constants.
 int lk_debug_read(lk_handle h, int what, void* dst, size_t bytes) {
     if (!h || !dst) return LK_ERR_INVALID_ARG;
-    if (what == 4) {  // debug records of the warp-specialised kernel (page-locked: readable while it runs)
-        if (!h->h_wdbg.p) return LK_ERR_NOT_READY;
-        std::memcpy(dst, h->h_wdbg.p, std::min(bytes, (size_t)256 * 16 * 8 * 8));
-        return LK_OK;
-    }
     if (what == 3) {  // host-side phase times of lk_scan_update (ns, accumulated) — reading resets them
         std::memcpy(dst, h->hprof, std::min(bytes, sizeof(h->hprof)));
         std::memset(h->hprof, 0, sizeof(h->hprof));
         return LK_OK;
     }
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     DevBuf* b = what == 0 ? &h->partial : (what == 1 ? &h->sc : &h->trace);
     if (bytes > b->cap) bytes = b->cap;
     LK_CUDA(h, cudaMemcpy(dst, b->p, bytes, cudaMemcpyDeviceToHost));
@@ -370,6 +376,7 @@ int lk_debug_read(lk_handle h, int what, void* dst, size_t bytes) {
 int lk_sync(lk_handle h) {
     if (!h) return LK_ERR_INVALID_ARG;
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     LK_CUDA(h, cudaStreamSynchronize(h->stream));
     return LK_OK;
 }
@@ -387,6 +394,7 @@ int lk_map_reserve(lk_handle h, uint64_t max_roots, uint64_t max_nodes, uint64_t
 int lk_map_upload(lk_handle h, const void* blob, size_t bytes) {
     if (!h || !blob) return fail(h, LK_ERR_INVALID_ARG, "null argument");
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     std::string err;
     int rc = map_upload_blob(h->map, h->g, blob, bytes, h->stream, err);
     return rc ? fail(h, rc, err) : LK_OK;
@@ -395,6 +403,7 @@ int lk_map_upload(lk_handle h, const void* blob, size_t bytes) {
 int lk_map_stats(lk_handle h, uint64_t out[4]) {
     if (!h || !out) return LK_ERR_INVALID_ARG;
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     std::string err;
     uint64_t planes = 0, live = 0;
     int rc = map_count_planes(h->map, &planes, &live, h->stream, err);
@@ -409,6 +418,7 @@ int lk_map_stats(lk_handle h, uint64_t out[4]) {
 int lk_map_download(lk_handle h, void* blob, size_t capacity, size_t* bytes_out) {
     if (!h) return LK_ERR_INVALID_ARG;
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     std::string err;
     int rc = map_download_blob(h->map, blob, capacity, bytes_out, h->stream, err);
     return rc ? fail(h, rc, err) : LK_OK;
@@ -419,6 +429,7 @@ int lk_map_build(lk_handle h, const float* xyz_world, const float* xyz_body, siz
     if (!h || !rot || !rot_cov || !pos_cov || (n && (!xyz_world || !xyz_body))) return fail(h, LK_ERR_INVALID_ARG, "null argument");
     if (n >= (1ull << 31)) return fail(h, LK_ERR_CAPACITY, "too many points for one build");
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     cudaStream_t s = h->stream;
     LK_CUDA(h, h->pts.ensure(std::max<size_t>(n, 1) * 12));
     LK_CUDA(h, h->world.ensure(std::max<size_t>(n, 1) * 12));
@@ -449,10 +460,12 @@ static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P
                       const uint32_t* scan_bucket_ptr, const uint32_t* bucket_offsets, const double* bucket_times,
                       bool sync_after, bool want_direct = false, float* world_out = nullptr) {
     if (!h) return LK_ERR_INVALID_ARG;
+    h->prev_fused = false;
     h->direct = h->direct_ran = h->inline_ok = false;
     if (batch <= 0 || !x || !P || !Q || !clk || !scan_offsets || !scan_bucket_ptr || !bucket_offsets || !bucket_times)
         return fail(h, LK_ERR_INVALID_ARG, "null / empty batch argument");
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     const uint64_t total = scan_offsets[batch];
     if (total && !pts) return fail(h, LK_ERR_INVALID_ARG, "pts is null");
     // host-side tables: chunks grouped by step (bucket rank inside its scan)
@@ -467,8 +480,8 @@ static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P
                 return fail(h, LK_ERR_INVALID_ARG, "bucket_offsets outside their scan");
         }
     }
-    // 60 groups split evenly over the double-buffered kernel's 6 (or 5) warps; 64 over the others' 8
-    const uint32_t big_chunk = h->use_ws >= 2 ? 1920u : 2048u;
+    // 60 groups split evenly over the pipelined kernel's 6 warps
+    const uint32_t big_chunk = 1920u;
     auto build_tables = [&](bool throughput, std::vector<ChunkDesc>& chunks, std::vector<StepInit>& inits) {
         chunks.clear();
         inits.assign((size_t)max_buckets * batch, StepInit());
@@ -526,9 +539,10 @@ static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P
     LK_CUDA(h, h->sc.ensure((size_t)batch * sizeof(ScanConst)));
     LK_CUDA(h, h->step.ensure((size_t)batch * sizeof(ScanStep)));
     LK_CUDA(h, h->partial.ensure(2 * std::max<size_t>(std::max(chunks.size(), chunksL.size()), 1) * PARTIAL_STRIDE * 8));
-    if (!h->bar.p) {
-        LK_CUDA(h, h->bar.ensure(64));
-        LK_CUDA(h, cudaMemsetAsync(h->bar.p, 0, 64, h->stream));
+    if (!h->ll.p) {
+        LK_CUDA(h, h->ll.ensure(LL_BYTES));
+        LK_CUDA(h, cudaMemsetAsync(h->ll.p, 0, LL_BYTES, h->stream));
+        h->ll_epoch = 1;
     }
     LK_CUDA(h, h->ticket.ensure((size_t)batch * 4));
     // ---- small inputs: one pinned block, one H2D copy ------------------------------------------
@@ -611,9 +625,11 @@ int lk_batch_stage(lk_handle h, int batch, const lk_state* x, const double* P, c
 int lk_timer_start(lk_handle h) {
     if (!h) return LK_ERR_INVALID_ARG;
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     h->nev = 0;
     h->acc_launches = 0;
     h->acc_residual_launches = 0;
+    h->prev_fused = false;
     LK_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     return LK_OK;
 }
@@ -622,6 +638,7 @@ int lk_timer_stop(lk_handle h, float* total_ms, float* residual_kernel_ms, uint3
                   uint32_t* n_residual_launches) {
     if (!h) return LK_ERR_INVALID_ARG;
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     LK_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     LK_CUDA(h, cudaStreamSynchronize(h->stream));
     LK_CUDA(h, cudaGetLastError());
@@ -690,20 +707,21 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         }
     }
     if (!h->map.ready()) return fail(h, LK_ERR_NOT_READY, "no map: call lk_map_upload or lk_map_build first");
-    if (count == 1 && h->use_fused && h->max_chunk_pts <= 256 && !update_map) {
-        // one scan: the whole bucket loop in ONE persistent cooperative kernel (lk_fused.cu)
-        uint32_t max_chunks = 1;
+    uint32_t max_chunks = 1;
+    if (count == 1)
         for (uint32_t k = 0; k < h->n_steps; ++k) {
             const StepInit& in = h->h_inits[(size_t)k * batch + first];
             max_chunks = std::max(max_chunks, in.chunk_end - in.chunk_begin);
         }
-        uint32_t grid = std::min<uint32_t>(max_chunks, (uint32_t)std::max(1, fused_max_blocks(h->device)));
+    if (count == 1 && h->use_fused && h->max_chunk_pts <= 256 && !update_map && max_chunks <= (uint32_t)fused_max_blocks(h->device)) {
+        // one scan: the whole bucket loop in ONE persistent kernel, one chunk per block (lk_fused.cu)
+        const uint32_t grid = max_chunks;
         FusedArgs fa;
         std::memset(&fa, 0, sizeof(fa));
         fa.pts = h->direct ? h->direct_pts : h->pts.as<float4>();
         fa.world = h->direct ? h->direct_world : h->world.as<float4>();
-        fa.chunks = h->chunks.as<ChunkDesc>();
         fa.inits = h->stepinit.as<StepInit>();
+        FusedInline* inl = nullptr;
         if (h->inline_ok) {
             // staged by stage_impl in the packed host block: chunks | inits | x | P | clk | Q
             auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -712,17 +730,15 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
             const size_t o_x = o_inits + al(std::max<size_t>(h->h_inits.size(), 1) * sizeof(StepInit));
             const size_t o_P = o_x + al(sizeof(lk_state));
             const size_t o_clk = o_P + al(900 * 8);
-            fa.inline_in = 1;
-            std::memcpy(fa.inl.x, hs + o_x, sizeof(fa.inl.x));
-            std::memcpy(fa.inl.P, hs + o_P, sizeof(fa.inl.P));
-            std::memcpy(fa.inl.clk, hs + o_clk, sizeof(fa.inl.clk));
-            std::memcpy(fa.inl.steps, h->h_inits.data(), h->h_inits.size() * sizeof(StepInit));
+            inl = &h->inl;
+            std::memcpy(inl->x, hs + o_x, sizeof(inl->x));
+            std::memcpy(inl->P, hs + o_P, sizeof(inl->P));
+            std::memcpy(inl->clk, hs + o_clk, sizeof(inl->clk));
+            std::memcpy(inl->steps, h->h_inits.data(), h->h_inits.size() * sizeof(StepInit));
         }
         fa.batch = batch;
         fa.n_steps = h->n_steps;
         fa.scan = first;
-        fa.partial = h->partial.as<double>();
-        fa.partial_stride = (size_t)std::max<uint32_t>(h->total_chunks, 1) * PARTIAL_STRIDE;
         fa.x_in = h->x_in.as<double>();
         fa.P_in = h->P_in.as<double>();
         fa.clk_in = h->clk_in.as<lk_stream_clock>();
@@ -731,9 +747,18 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         fa.P = h->P.as<double>();
         fa.clk = h->clk.as<lk_stream_clock>();
         fa.n_eff = h->n_eff.as<uint32_t>();
-        fa.bar = h->bar.as<uint32_t>();
-        fa.parity = h->fused_parity;
-        h->fused_parity ^= 1;
+        // tags of the flagged rows: one per (step, iteration); restart (with a cleared buffer) long before the 32-bit wrap
+        const uint32_t need = h->n_steps * (uint32_t)iters + 1u;
+        if (h->ll_epoch > 0xE0000000u || need > 0x10000000u) {
+            if (need > 0x10000000u) return fail(h, LK_ERR_INVALID_ARG, "steps x iters too large for one launch");
+            LK_CUDA(h, cudaMemsetAsync(h->ll.p, 0, LL_BYTES, s));
+            h->ll_epoch = 1;
+            h->prev_fused = false;
+        }
+        fa.ll.chunk_rows = h->ll.as<ulonglong2>();
+        fa.ll.group_rows = h->ll.as<ulonglong2>() + (size_t)2 * LL_MAX_CHUNKS * LL_ROW;
+        fa.epoch = h->ll_epoch;
+        h->ll_epoch += need;
         fa.iters = iters;
         fa.lane_cache = h->lane_cache;
         fa.mv.slots = h->map.slots;
@@ -749,14 +774,30 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         fa.ecfg = h->ec;
         fa.trace = h->trace_on ? h->trace.as<unsigned long long>() : nullptr;
         fa.g = h->g;
-        if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
-        LK_CUDA(h, launch_scan_fused(fa, grid, s, h->coop_launch != 0));
-        if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
+        if (h->kernel_timing) { cudaEventRecord(kev_get(h, h->nev++), s); h->prev_fused = false; }
+        const int mode = h->coop_launch ? FUSED_LAUNCH_COOPERATIVE : ((h->pdl && h->prev_fused) ? FUSED_LAUNCH_PDL : FUSED_LAUNCH_PLAIN);
+        {
+            // Blocks of this kernel poll for each other's rows: two such grids must never share the device half
+            // resident. Launches of one stream are ordered by the stream; launches of different handles of this
+            // process are ordered here (the later one waits for everything the earlier stream has queued).
+            FusedGate& gate = fused_gate(h->device);
+            std::lock_guard<std::mutex> lock(gate.m);
+            if (gate.last && gate.last != s) {
+                if (!gate.ev) LK_CUDA(h, cudaEventCreateWithFlags(&gate.ev, cudaEventDisableTiming));
+                LK_CUDA(h, cudaEventRecord(gate.ev, gate.last));
+                LK_CUDA(h, cudaStreamWaitEvent(s, gate.ev, 0));
+            }
+            gate.last = s;
+            LK_CUDA(h, launch_scan_fused(fa, inl, grid, s, mode));
+        }
+        h->prev_fused = true;
+        if (h->kernel_timing) { cudaEventRecord(kev_get(h, h->nev++), s); h->prev_fused = false; }
         ++h->acc_launches;
         ++h->acc_residual_launches;
         h->direct_ran = h->direct;
         return LK_OK;
     }
+    h->prev_fused = false;
     if (h->direct) return fail(h, LK_ERR_CUDA, "internal: direct staging without the per-scan kernel");
     // >= 2 scans per call: the throughput family and its chunk table (see chunk_size_for)
     const bool big = count >= 2 && !h->h_initsL.empty();
@@ -810,13 +851,12 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
             if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
             // latency variant only for a single scan: the kernel family must not depend on how a batch is
             // sharded (bitwise-reproducible sums)
-            if (count >= 2 && h->use_ws) {
-                if (h->use_ws >= 2) launch_residual_stream2(ra, c1 - c0, s);
-                else launch_residual_ws(ra, c1 - c0, h->n_sms, s);
+            if (count >= 2 || h->max_chunk_pts > 256) {
+                launch_residual_stream2(ra, c1 - c0, s);
                 launch_scan_tail(ra, first, count, s);
                 if (c1 > c0) ++h->acc_launches;
             } else {
-                launch_residual(ra, c1 - c0, false, count == 1 && h->max_chunk_pts <= 256, s);
+                launch_residual(ra, c1 - c0, false, true, s);
             }
             if (h->kernel_timing) cudaEventRecord(kev_get(h, h->nev++), s);
             if (c1 > c0) { ++h->acc_launches; ++h->acc_residual_launches; }
@@ -880,6 +920,7 @@ int lk_batch_fetch(lk_handle h, lk_state* x_out, double* P_out, lk_stream_clock*
     if (!h) return LK_ERR_INVALID_ARG;
     if (h->batch <= 0) return fail(h, LK_ERR_NOT_READY, "nothing staged");
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     cudaStream_t s = h->stream;
     const int batch = h->batch;
     const bool small = x_out || P_out || clk_out || n_effective_out;
@@ -948,6 +989,7 @@ int lk_debug_residuals(lk_handle h, const lk_state* x, const double* P, const fl
     int rc = lk_batch_stage(h, 1, x, P, Q.data(), &clk, pts, so, sb, bo, bt);
     if (rc) return rc;
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     cudaStream_t s = h->stream;
     size_t nn = std::max<size_t>(n, 1);
     LK_CUDA(h, h->dbg_ok.ensure(nn));
@@ -998,6 +1040,7 @@ int lk_predict(lk_handle h, int batch, lk_state* x_inout, double* P_inout, const
                int prop_state, int prop_cov) {
     if (!h || batch <= 0 || !x_inout || !P_inout || !Q || !dt) return fail(h, LK_ERR_INVALID_ARG, "null argument");
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     cudaStream_t s = h->stream;
     LK_CUDA(h, h->fx.ensure((size_t)batch * sizeof(lk_state)));
     LK_CUDA(h, h->fP.ensure((size_t)batch * 900 * 8));
@@ -1048,6 +1091,7 @@ int lk_update_by_points(lk_handle h, lk_state* x_inout, double* P_inout, uint32_
                         const double* pt_R) {
     if (!h || !x_inout || !P_inout || (n && (!pt_h || !pt_z || !pt_R))) return fail(h, LK_ERR_INVALID_ARG, "null argument");
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     if (n == 0) return LK_OK;  // KILO.cc:188: no residual, no update
     int rc = filter_upload(h, x_inout, P_inout, nullptr, nullptr);
     if (rc) return rc;
@@ -1067,6 +1111,7 @@ int lk_obs_imu(lk_handle h, lk_state* x_inout, double* P_inout, const double* Q,
                const lk_imu_meas* imu, uint32_t n, double gravity, double acc_norm) {
     if (!h || !x_inout || !P_inout || !Q || !clk_inout || (n && !imu)) return fail(h, LK_ERR_INVALID_ARG, "null argument");
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     if (n == 0) return LK_OK;
     int rc = filter_upload(h, x_inout, P_inout, Q, clk_inout);
     if (rc) return rc;
@@ -1081,6 +1126,7 @@ int lk_obs_kinimu(lk_handle h, lk_state* x_inout, double* P_inout, const double*
                   const lk_kinimu_meas* kin, uint32_t n, double gravity, double acc_norm) {
     if (!h || !x_inout || !P_inout || !Q || !clk_inout || (n && !kin)) return fail(h, LK_ERR_INVALID_ARG, "null argument");
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     if (n == 0) return LK_OK;
     int rc = filter_upload(h, x_inout, P_inout, Q, clk_inout);
     if (rc) return rc;
@@ -1104,6 +1150,7 @@ int lk_process_scan(lk_handle h, lk_state* x_inout, double* P_inout, const doubl
     int rc = stage_impl(h, 1, x_inout, P_inout, Q, clk_inout, pts, so, sb, bucket_offsets, bucket_times, false);
     if (rc) return rc;
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     MeasQueue mq;
     std::vector<double> stamps(n_meas);
     if (n_meas) {
@@ -1144,6 +1191,7 @@ int lk_decode_pointcloud2(lk_handle h, const uint8_t* data, uint32_t n_points, c
         L.off_z + 4 > L.point_step || L.off_intensity + 4 > L.point_step || L.off_time + tsz > L.point_step)
         return fail(h, LK_ERR_INVALID_ARG, "field layout does not fit point_step");
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     auto host_time = [&](uint32_t i) {
         const uint8_t* p = data + (size_t)i * L.point_step + L.off_time;
         if (L.lidar_type == LK_LIDAR_VELODYNE) { float t; std::memcpy(&t, p, 4); return (double)t; }
@@ -1166,6 +1214,7 @@ int lk_preprocess_scan(lk_handle h, const float* pts_in, uint32_t n_in, float le
         return fail(h, LK_ERR_INVALID_ARG, "null argument");
     if (!(leaf_size > 0)) return fail(h, LK_ERR_INVALID_ARG, "leaf size must be positive");
     cudaSetDevice(h->device);
+    h->prev_fused = false;
     std::string err;
     int rc = preprocess_scan_device(pts_in, n_in, leaf_size, pts_out, n_out, bucket_offsets, bucket_curvature, n_buckets, h->stream, err);
     return rc ? fail(h, rc, err) : LK_OK;

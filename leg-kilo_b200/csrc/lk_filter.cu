@@ -174,26 +174,24 @@ __global__ void __launch_bounds__(FB) k_update_by_points(double* x, double* P, u
 
 }  // namespace
 
+static void obs_attrs() {  // function attributes are per device
+    static PerDeviceOnce once;
+    if (once.first()) {
+        cudaFuncSetAttribute(k_filter_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ObsSmem));
+        cudaFuncSetAttribute(k_update_by_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ObsSmem));
+    }
+}
+
 void launch_filter_obs(double* x, double* P, const double* Q, lk_stream_clock* clk, const lk_imu_meas* imu,
                        const lk_kinimu_meas* kin, uint32_t n, const lk_eskf_cfg& cfg, double gravity, double acc_norm,
                        cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_filter_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ObsSmem));
-        cudaFuncSetAttribute(k_update_by_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ObsSmem));
-        attr = true;
-    }
+    obs_attrs();
     k_filter_obs<<<1, FB, sizeof(ObsSmem), s>>>(x, P, Q, clk, imu, kin, n, cfg, gravity, acc_norm);
 }
 
 void launch_update_by_points(double* x, double* P, uint32_t n, const double* h, const double* z, const double* r,
                              cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_filter_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ObsSmem));
-        cudaFuncSetAttribute(k_update_by_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ObsSmem));
-        attr = true;
-    }
+    obs_attrs();
     k_update_by_points<<<1, FB, sizeof(ObsSmem), s>>>(x, P, n, h, z, r);
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "lk_device.cuh"
+#include "lk_llsync.cuh"
 
 namespace lk {
 
@@ -39,16 +40,15 @@ struct ResidualArgs {
     double* dbg_R;
     int32_t* dbg_key;
     unsigned long long* trace;  // optional %globaltimer stamps: 8 per block + 8 for the tail
-    unsigned long long* wdbg;   // optional page-locked debug records of the warp-specialised kernel (16 x 4 per block)
     Globals g;
 };
 
-// single: every chunk of the launch holds at most 128 points (one point per thread)
+// single: every chunk of the launch holds at most 256 points (one point per thread, one pass); otherwise blocks make
+// several passes over their chunk
 void launch_residual(const ResidualArgs& a, uint32_t n_chunks, bool debug, bool single, cudaStream_t s);
-// throughput family: warp-specialised persistent residual pass (lk_stream_ws.cu) writing one partial row per
-// chunk, then the per-scan solve for scans [scan_first, scan_first + n_scans) (lk_residual.cu)
-void launch_residual_ws(const ResidualArgs& a, uint32_t n_chunks, int n_sms, cudaStream_t s);
-void launch_residual_stream2(const ResidualArgs& a, uint32_t n_chunks, cudaStream_t s);  // lk_stream2.cu
+// throughput family: pipelined residual pass (lk_stream2.cu) writing one partial row per chunk, then the per-scan
+// solve for scans [scan_first, scan_first + n_scans) (lk_residual.cu)
+void launch_residual_stream2(const ResidualArgs& a, uint32_t n_chunks, cudaStream_t s);
 void launch_scan_tail(const ResidualArgs& a, uint32_t scan_first, uint32_t n_scans, cudaStream_t s);
 
 struct PredictArgs {
@@ -94,24 +94,24 @@ void launch_update_by_points(double* x, double* P, uint32_t n, const double* h, 
 
 // ---- fused per-scan persistent kernel (lk_fused.cu) -------------------------------------------
 constexpr int FUSED_INLINE_STEPS = 64;
-// Small inputs carried in the kernel's parameter block (no staging copy before the launch).
+// Small inputs carried in the kernel's parameter block (direct mode: no staging copy before the launch).
 struct FusedInline {
     double x[36];
     double P[900];
     double clk[2];
     StepInit steps[FUSED_INLINE_STEPS];
 };
+struct FusedNoInline {
+    int unused;
+};
 
 struct FusedArgs {
     const float4* pts;    // device memory, or page-locked host memory read in place (each point is read once)
     float4* world;
-    const ChunkDesc* chunks;
-    const StepInit* inits;  // [n_steps][batch]
+    const StepInit* inits;  // [n_steps][batch] (unused with inline inputs)
     int batch;
     uint32_t n_steps;
     uint32_t scan;
-    double* partial;         // 2 x partial_stride doubles (double-buffered by iteration parity)
-    size_t partial_stride;
     const double* x_in;
     const double* P_in;
     const lk_stream_clock* clk_in;
@@ -120,8 +120,8 @@ struct FusedArgs {
     double* P;
     lk_stream_clock* clk;
     uint32_t* n_eff;
-    uint32_t* bar;  // [2] grid-barrier counters, used alternately by consecutive launches
-    int parity;
+    LLView ll;       // flagged rows of the barrier-free all-reduce (lk_llsync.cuh)
+    uint32_t epoch;  // tag of this launch's first iteration; the launch uses epoch .. epoch + n_steps * iters - 1
     int iters;
     int lane_cache;  // keep per-lane lookups / staged records across the iterations of a bucket
     MapView mv;
@@ -132,11 +132,24 @@ struct FusedArgs {
     lk_eskf_cfg ecfg;
     unsigned long long* trace;  // optional: 32 %globaltimer stamps per block
     Globals g;
-    int inline_in;  // x_in / P_in / clk_in / inits come from `inl`
-    FusedInline inl;
 };
+enum { FUSED_LAUNCH_PLAIN = 0, FUSED_LAUNCH_COOPERATIVE = 1, FUSED_LAUNCH_PDL = 2 };
 size_t fused_smem_bytes();
 int fused_max_blocks(int device);
-cudaError_t launch_scan_fused(const FusedArgs& a, uint32_t grid, cudaStream_t s, bool cooperative);
+// inl != null: the filter inputs and the step table ride in the parameter block
+cudaError_t launch_scan_fused(const FusedArgs& a, const FusedInline* inl, uint32_t grid, cudaStream_t s, int mode);
+
+// Per-device "already done" latch for cudaFuncSetAttribute-style one-time setup (function attributes are per device).
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first() {
+        int d = 0;
+        cudaGetDevice(&d);
+        if (d < 0 || d >= 64) return true;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
 
 }  // namespace lk

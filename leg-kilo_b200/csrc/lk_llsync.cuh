@@ -1,0 +1,105 @@
+// lk_llsync.cuh — grid-wide all-reduce of one 32-double row per block WITHOUT a barrier: rows travel
+// through global memory in a flagged ("low-latency") format — every double is split into two 8-byte
+// words {low 32 bits | tag << 32, high 32 bits | tag << 32} stored with ONE 16-byte store. Aligned 8-byte
+// stores are single-copy atomic, so a reader that finds the expected tag in both words holds the whole
+// value: data and "ready" flag arrive together, there is no release fence, no counter and no second
+// round trip to read the rows after a barrier. The tag is a per-handle epoch that grows with every
+// (launch, iteration), so stale rows of earlier iterations never match; two buffers alternate by
+// iteration parity (a block writes iteration i+2 only after it has seen every row of iteration i+1,
+// i.e. after every block has finished reading iteration i).
+//
+// Summation order (shared with the multi-kernel path, lk_solve.cuh: block_sum_partials):
+//   total = sum over groups g ascending of ( sum over the rows of group g ascending ),
+//   group g = chunks [g*LK_GROUP, (g+1)*LK_GROUP) of the bucket — a function of the bucket alone.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lk {
+
+constexpr int LK_GROUP = 8;          // chunk rows per group (level-1 fan-in)
+constexpr int LL_ROW = 32;           // slots (doubles) per row
+constexpr int LL_MAX_CHUNKS = 160;   // >= SM count: the fused kernel runs one chunk per block
+constexpr int LL_MAX_GROUPS = (LL_MAX_CHUNKS + LK_GROUP - 1) / LK_GROUP;
+
+struct LLView {
+    ulonglong2* chunk_rows;  // [2][LL_MAX_CHUNKS][LL_ROW]
+    ulonglong2* group_rows;  // [2][LL_MAX_GROUPS][LL_ROW]
+};
+constexpr size_t LL_BYTES = (size_t)2 * (LL_MAX_CHUNKS + LL_MAX_GROUPS) * LL_ROW * sizeof(ulonglong2);
+
+__device__ __forceinline__ void ll_store(ulonglong2* p, double v, uint32_t tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long t = (unsigned long long)tag << 32;
+    const unsigned long long w0 = (b & 0xffffffffull) | t, w1 = (b >> 32) | t;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
+}
+
+__device__ __forceinline__ bool ll_load(const ulonglong2* p, uint32_t tag, double& v) {
+    unsigned long long w0, w1;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+    v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    return (uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag;
+}
+
+// Element `lane` of rows [r0, r0 + n) (n <= N), summed in ascending row order starting from 0.0. All loads are
+// issued before any is inspected; rows that have not arrived are re-polled. Called by one full warp.
+template <int N>
+__device__ __forceinline__ double ll_sum_rows(const ulonglong2* rows, uint32_t r0, uint32_t n, uint32_t tag, int lane) {
+    double v[N];
+    uint32_t pending = n >= 32u ? 0xffffffffu : ((1u << n) - 1u);
+    while (pending) {
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+            if (pending & (1u << k)) {
+                double t;
+                if (ll_load(rows + (size_t)(r0 + k) * LL_ROW + lane, tag, t)) {
+                    v[k] = t;
+                    pending &= ~(1u << k);
+                }
+            }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+        if ((uint32_t)k < n) s += v[k];
+    return s;
+}
+
+// The all-reduce. `v` = this block's row element `lane` (warp 0 calls, all 32 lanes). Block b owns chunk b of the
+// n_chunks chunks of the bucket (blocks with b >= n_chunks contribute nothing but still receive the total).
+// Returns the total of element `lane` in the fixed grouped order.
+__device__ __forceinline__ double ll_allreduce(const LLView& ll, uint32_t parity, uint32_t tag, uint32_t b, uint32_t n_chunks,
+                                               double v, int lane) {
+    ulonglong2* crows = ll.chunk_rows + (size_t)parity * LL_MAX_CHUNKS * LL_ROW;
+    ulonglong2* grows = ll.group_rows + (size_t)parity * LL_MAX_GROUPS * LL_ROW;
+    if (b < n_chunks) ll_store(crows + (size_t)b * LL_ROW + lane, v, tag);
+    const uint32_t n_groups = (n_chunks + LK_GROUP - 1) / LK_GROUP;
+    if (b < n_chunks && (b % LK_GROUP) == 0) {  // leader of group b / LK_GROUP
+        const uint32_t n = min((uint32_t)LK_GROUP, n_chunks - b);
+        double s = 0.0;
+        s += v;  // own row first (chunk b), then the others ascending: the same sequence as ll_sum_rows over all of them
+        if (n > 1) {
+            double r[LK_GROUP - 1];
+            uint32_t pending = (1u << (n - 1)) - 1u;
+            while (pending) {
+#pragma unroll
+                for (int k = 0; k < LK_GROUP - 1; ++k)
+                    if (pending & (1u << k)) {
+                        double t;
+                        if (ll_load(crows + (size_t)(b + 1 + k) * LL_ROW + lane, tag, t)) {
+                            r[k] = t;
+                            pending &= ~(1u << k);
+                        }
+                    }
+            }
+#pragma unroll
+            for (int k = 0; k < LK_GROUP - 1; ++k)
+                if ((uint32_t)k < n - 1) s += r[k];
+        }
+        ll_store(grows + (size_t)(b / LK_GROUP) * LL_ROW + lane, s, tag);
+    }
+    return ll_sum_rows<LL_MAX_GROUPS>(grows, 0, n_groups, tag, lane);
+}
+
+}  // namespace lk

@@ -92,13 +92,10 @@ __global__ void __launch_bounds__(BLOCK, (DEBUG || SINGLE) ? 1 : 2) k_residual(c
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc[i] = 0.0;
     uint32_t phase = 0;
-    LaneCache lc;
-    lc.have = 0;
-    lc.fail = 0;
     for (uint32_t off = 0; off < cd.count; off += BLOCK) {
         const uint32_t n = min((uint32_t)BLOCK, cd.count - off);
-        block_points_pass<BLOCK, DEBUG, false>(&rs->pass, phase, a.pts + cd.start + off, n, (size_t)cd.start + off, s_sc,
-                                               mv, a.g, acc, dbg, lc);
+        block_points_pass<BLOCK, DEBUG>(&rs->pass, phase, a.pts + cd.start + off, n, (size_t)cd.start + off, s_sc, mv, a.g,
+                                        acc, dbg);
         if (SINGLE) break;
     }
     if (DEBUG) return;
@@ -134,62 +131,7 @@ __global__ void __launch_bounds__(BLOCK, (DEBUG || SINGLE) ? 1 : 2) k_residual(c
     }
 }
 
-constexpr int STREAM_MAXPTS = 2048;  // largest chunk lk_api.cu hands out
-
-union StreamUnion {  // the tail runs after the streaming loop: same storage
-    StreamSmem<BLOCK, STREAM_MAXPTS> stream;
-    TailSmem tail;
-};
-
-// Throughput variant for large batches: warps stream their 32-point groups independently, records
-// are staged by cooperative async copies, fallback points are finished in bulk, 2 CTAs per SM.
-__global__ void __launch_bounds__(BLOCK, 2) k_residual_stream(const __grid_constant__ ResidualArgs a) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ ScanConst s_sc;
-    __shared__ uint32_t s_last;
-    StreamUnion* su = reinterpret_cast<StreamUnion*>(s_raw);
-    TailSmem* ts = &su->tail;
-    const int tid = threadIdx.x;
-    const ChunkDesc cd = a.chunks[a.chunk_first + blockIdx.x];
-    if (tid < (int)(sizeof(ScanConst) / sizeof(double)))
-        reinterpret_cast<double*>(&s_sc)[tid] = reinterpret_cast<const double*>(a.sc + cd.scan)[tid];
-    if (tid == 0) su->stream.n_fb = 0;
-    __syncthreads();
-    MapView mv;
-    mv.slots = a.slots; mv.hash_mask = a.hash_mask; mv.nodes = a.nodes;
-    double acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.0;
-    block_points_stream<BLOCK, STREAM_MAXPTS>(&su->stream, a.pts + cd.start, cd.count, s_sc, mv, a.g, acc);
-
-    const int lane = tid & 31, warp = tid >> 5;
-    double* s_red = ts->slice;
-    double tot = warp_transpose_sum(acc, lane);
-    __syncthreads();
-    s_red[warp * 32 + lane] = tot;
-    __syncthreads();
-    if (tid < 32) {
-        double v = 0.0;
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) v += s_red[w * 32 + tid];
-        a.partial[(size_t)(a.chunk_first + blockIdx.x) * PARTIAL_STRIDE + tid] = v;
-        __threadfence();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        const ScanStep* sp = a.step + cd.scan;
-        uint32_t n_chunks = sp->chunk_end - sp->chunk_begin;
-        uint32_t t = atomicAdd(a.ticket + cd.scan, 1u);
-        s_last = (t == n_chunks - 1) ? 1u : 0u;
-    }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        scan_solve(a, cd.scan, ts);
-    }
-}
-
-// The per-scan solve on its own (after lk_stream_ws.cu's residual pass): one block per scan.
+// The per-scan solve on its own (after lk_stream2.cu's residual pass): one block per scan.
 __global__ void __launch_bounds__(BLOCK) k_scan_tail(const __grid_constant__ ResidualArgs a, const uint32_t scan_first) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     TailSmem* ts = reinterpret_cast<TailSmem*>(s_raw);
@@ -203,38 +145,27 @@ __global__ void __launch_bounds__(BLOCK) k_scan_tail(const __grid_constant__ Res
 
 void launch_scan_tail(const ResidualArgs& a, uint32_t scan_first, uint32_t n_scans, cudaStream_t s) {
     if (n_scans == 0) return;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_scan_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem));
-        attr = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(k_scan_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem));
     k_scan_tail<<<n_scans, BLOCK, sizeof(TailSmem), s>>>(a, scan_first);
 }
 
 void launch_residual(const ResidualArgs& a, uint32_t n_chunks, bool debug, bool single, cudaStream_t s) {
     if (n_chunks == 0) return;
-    static bool attr_set = false;
+    static PerDeviceOnce once;
     const size_t smem = sizeof(ResidualSmem);
-    if (!attr_set) {
+    if (once.first()) {
         cudaFuncSetAttribute(k_residual<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_residual<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_residual<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_residual<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        attr_set = true;
     }
     if (debug)
         k_residual<true, false><<<n_chunks, BLOCK, smem, s>>>(a);
     else if (single)
         k_residual<false, true><<<n_chunks, BLOCK, smem, s>>>(a);
-    else {
-        static bool attr2 = false;
-        if (!attr2) {
-            cudaFuncSetAttribute(k_residual_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamUnion));
-            cudaFuncSetAttribute(k_residual_stream, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            attr2 = true;
-        }
-        k_residual_stream<<<n_chunks, BLOCK, sizeof(StreamUnion), s>>>(a);
-    }
+    else
+        k_residual<false, false><<<n_chunks, BLOCK, smem, s>>>(a);
 }
 
 // ---- re-projection with the updated state (KILO.cc:216-224) ---------------------------------

@@ -4,6 +4,7 @@
 // (SURVEY §8a a8, Appendix A.5), followed by State::operator+= (eskf.cc:18-29) and, on the last
 // iteration, P <- P - K H P[0:6,:] (no symmetrisation, as the reference).
 #pragma once
+#include "lk_llsync.cuh"
 #include "lk_point.cuh"
 
 namespace lk {
@@ -21,42 +22,46 @@ struct BlockFilter {
     double KH[180];
 };
 
-// Deterministic sum of per-chunk partial rows [c0, c1): warp w takes rows w, w+nw, ... (all loads
-// of a warp issued before the first add), then the per-warp slices are added in fixed order.
-// `slice` must hold nwarps*32 doubles. Result in out[0..31]. All threads of the block call.
+// Deterministic sum of the per-chunk partial rows [c0, c1) in the grouped order every path shares (lk_llsync.cuh):
+//   total = sum over groups g ascending of ( sum over the rows of group g ascending ), LK_GROUP rows per group.
+// Warp w forms the sum of group g0 + w (all loads of a group issued before the first add), the group sums are then
+// added in ascending order. `slice` must hold nwarps*32 doubles. Result in out[0..31]. All threads of the block call.
 template <int NWARPS>
 __device__ __forceinline__ void block_sum_partials(const double* partial, uint32_t c0, uint32_t c1, double* slice,
                                                    double* out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double acc = 0.0;
-    uint32_t c = c0 + warp;
-    // 16 rows per round (all loads issued before the first add; the adds keep row order, so the result does
-    // not depend on the round size)
-    for (; c < c1; c += 16 * NWARPS) {
-        const double* p = partial + (size_t)c * PARTIAL_STRIDE + lane;
-        double v[16];
+    const uint32_t n = c1 - c0, ng = (n + LK_GROUP - 1) / LK_GROUP;
+    double tot = 0.0;
+    for (uint32_t g0 = 0; g0 < ng; g0 += NWARPS) {
+        const uint32_t g = g0 + (uint32_t)warp;
+        if (g < ng) {
+            const uint32_t r0 = c0 + g * LK_GROUP, m = min((uint32_t)LK_GROUP, c1 - r0);
+            const double* p = partial + (size_t)r0 * PARTIAL_STRIDE + lane;
+            double v[LK_GROUP];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = (c + u * NWARPS < c1) ? __ldcg(p + (size_t)u * NWARPS * PARTIAL_STRIDE) : 0.0;
+            for (int k = 0; k < LK_GROUP; ++k) v[k] = ((uint32_t)k < m) ? __ldcg(p + (size_t)k * PARTIAL_STRIDE) : 0.0;
+            double s = 0.0;
 #pragma unroll
-        for (int u = 0; u < 16; ++u)
-            if (c + u * NWARPS < c1) acc += v[u];
+            for (int k = 0; k < LK_GROUP; ++k)
+                if ((uint32_t)k < m) s += v[k];
+            slice[warp * 32 + lane] = s;
+        }
+        __syncthreads();
+        if (tid < 32) {
+#pragma unroll
+            for (int w = 0; w < NWARPS; ++w)
+                if (g0 + (uint32_t)w < ng) tot += slice[w * 32 + tid];
+        }
+        __syncthreads();
     }
-    slice[warp * 32 + lane] = acc;
-    __syncthreads();
-    if (tid < 32) {
-        double v = 0.0;
-#pragma unroll
-        for (int w = 0; w < NWARPS; ++w) v += slice[w * 32 + tid];
-        out[tid] = v;
-    }
+    if (tid < 32) out[tid] = tot;
     __syncthreads();
 }
 
-// The update itself. f->acc holds the reduced sums. Returns the residual count. All threads call.
-// Warp 0 carries the whole serial chain (A, M = I + A P66, Gauss-Jordan, delta, State (+)) with
-// warp-level synchronisation only; the block joins for the covariance update of the last iteration.
-template <int NTHREADS>
-__device__ __forceinline__ uint32_t block_solve_update(BlockFilter* f, bool last_iter, unsigned long long* clk = nullptr) {
+// The state half of the update. f->acc holds the reduced sums. Returns the residual count. All threads call.
+// Warp 0 carries the whole serial chain (A, M = I + A P66, Gauss-Jordan, delta, State (+)) with warp-level
+// synchronisation only, and leaves W = M^-1 A in f->W for the covariance half; ends with a block barrier.
+__device__ __forceinline__ uint32_t block_solve_state(BlockFilter* f, unsigned long long* clk = nullptr) {
 #define LK_SC(i) do { if (clk && threadIdx.x == 0) clk[i] = (unsigned long long)clock64(); } while (0)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double cnt = f->acc[ACC_CNT];
@@ -122,30 +127,40 @@ __device__ __forceinline__ uint32_t block_solve_update(BlockFilter* f, bool last
         }
         __syncthreads();
         LK_SC(6);
-        if (last_iter) {
-            // P <- P - (P6 W) P[0:6,:]   (eskf.cc:112, no symmetrisation)
-            for (int e = tid; e < 180; e += NTHREADS) {
-                f->Prow[e] = f->P[e];  // rows 0..5 are contiguous
-                int i = e / 6, j = e % 6;
-                double s = 0.0;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) s += f->P[i * 30 + k] * f->W[k * 6 + j];
-                f->KH[e] = s;
-            }
-            __syncthreads();
-            for (int e = tid; e < 900; e += NTHREADS) {
-                int i = e / 30, j = e % 30;
-                double s = 0.0;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) s += f->KH[i * 6 + k] * f->Prow[k * 30 + j];
-                f->P[e] -= s;
-            }
-            __syncthreads();
-        }
     }
-    LK_SC(7);
 #undef LK_SC
     return (uint32_t)(cnt + 0.5);
+}
+
+// The covariance half: P <- P - (P6 W) P[0:6,:]   (eskf.cc:112, no symmetrisation). All threads call.
+template <int NTHREADS>
+__device__ __forceinline__ void block_cov_update(BlockFilter* f) {
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 180; e += NTHREADS) {
+        f->Prow[e] = f->P[e];  // rows 0..5 are contiguous
+        int i = e / 6, j = e % 6;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s += f->P[i * 30 + k] * f->W[k * 6 + j];
+        f->KH[e] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < 900; e += NTHREADS) {
+        int i = e / 30, j = e % 30;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s += f->KH[i * 6 + k] * f->Prow[k * 30 + j];
+        f->P[e] -= s;
+    }
+    __syncthreads();
+}
+
+// Both halves (the covariance only after the last iteration). Returns the residual count.
+template <int NTHREADS>
+__device__ __forceinline__ uint32_t block_solve_update(BlockFilter* f, bool last_iter, unsigned long long* clk = nullptr) {
+    const uint32_t n = block_solve_state(f, clk);
+    if (n > 0 && last_iter) block_cov_update<NTHREADS>(f);
+    return n;
 }
 
 // ScanConst from a shared-memory filter. Threads 0..23.

@@ -195,11 +195,10 @@ __global__ void __launch_bounds__(S2_THREADS, 2) k_residual_stream2(const __grid
 
 void launch_residual_stream2(const ResidualArgs& a, uint32_t n_chunks, cudaStream_t s) {
     if (n_chunks == 0) return;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce once;
+    if (once.first()) {
         cudaFuncSetAttribute(k_residual_stream2<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S2Smem<6>));
         cudaFuncSetAttribute(k_residual_stream2<192>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        attr = true;
     }
     k_residual_stream2<192><<<n_chunks, 192, sizeof(S2Smem<6>), s>>>(a);
 }

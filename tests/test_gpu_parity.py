@@ -92,13 +92,12 @@ def test_single_scan_paths_agree_with_oracle(fused):
     globals()[key] = out
 
 
-@pytest.mark.parametrize("ws", [2, 1, 0])
-def test_throughput_family_chunk_edges_and_variants(ws):
-    """Calls with >= 2 scans take the throughput family: 1 920- / 2 048- / 256-point chunks, warps streaming 32-point
-    groups through a software pipeline (ws=2, default), a producer/consumer ring (ws=1) or one stage (ws=0). Scan
-    lengths sit on every edge of that machinery (one point, group and chunk boundaries +-1, several chunks, a warp
-    without work); every variant must reproduce the oracle's residual counts exactly and its state / covariance
-    within tolerance, whatever mixture of lengths shares the call."""
+def test_throughput_family_chunk_edges():
+    """Calls with >= 2 scans take the throughput family: 1 920- / 256-point chunks, warps streaming 32-point groups
+    through a software pipeline. Scan lengths sit on every edge of that machinery (one point, group and chunk
+    boundaries +-1, several chunks, a warp without work); the kernel must reproduce the oracle's residual counts
+    exactly and its state / covariance within tolerance, whatever mixture of lengths shares the call."""
+    ws = 2
     cfg, blob, scans = scenes.box_scene(batch=2, lidar=synth.OS64)
     base = np.concatenate(scans)
     assert len(base) > 8000
@@ -113,7 +112,6 @@ def test_throughput_family_chunk_edges_and_variants(ws):
     offs = np.concatenate([[0], np.cumsum([len(s) for s in pieces])]).astype(np.uint32)
     x0 = abi.default_states(B); P0 = abi.init_cov(B)
     eng = Engine(cfg)
-    eng.set_param("ws", ws)
     eng.map_upload(blob)
     out = eng.scan_update(x0, P0, abi.process_cov_Q(cfg), np.zeros(B, abi.CLOCK_DTYPE), pts, offs, np.zeros(B), iters=2)
     again = eng.scan_update(x0, P0, abi.process_cov_Q(cfg), np.zeros(B, abi.CLOCK_DTYPE), pts, offs, np.zeros(B), iters=2)
