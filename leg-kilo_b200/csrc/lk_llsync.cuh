@@ -35,68 +35,97 @@ __device__ __forceinline__ void ll_store(ulonglong2* p, double v, uint32_t tag) 
     asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
 }
 
-__device__ __forceinline__ bool ll_load(const ulonglong2* p, uint32_t tag, double& v) {
-    unsigned long long w0, w1;
-    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
-    v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
-    return (uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag;
-}
-
-// Element `lane` of rows [r0, r0 + n) (n <= N), summed in ascending row order starting from 0.0. All loads are
-// issued before any is inspected; rows that have not arrived are re-polled. Called by one full warp.
+// Element `lane` of rows [r0, r0 + n) (n <= N), summed in ascending row order starting from 0.0. Every poll round
+// issues ALL n loads back to back (independent, so they overlap in the memory system: one L2 round trip per round,
+// not one per row) and only then inspects the tags; the round repeats until every row carries the tag (rows never
+// change once published within an epoch, so re-reading the ones that already matched is harmless). One full warp.
 template <int N>
-__device__ __forceinline__ double ll_sum_rows(const ulonglong2* rows, uint32_t r0, uint32_t n, uint32_t tag, int lane) {
-    double v[N];
-    uint32_t pending = n >= 32u ? 0xffffffffu : ((1u << n) - 1u);
-    while (pending) {
+__device__ __forceinline__ double ll_sum_rows(const ulonglong2* rows, uint32_t r0, uint32_t n, uint32_t tag, int lane,
+                                              double first = 0.0, bool have_first = false) {
+    const ulonglong2* p = rows + (size_t)r0 * LL_ROW + lane;
+    unsigned long long w0[N], w1[N];
+    const unsigned long long want = ((unsigned long long)tag << 32);
+    bool all;
+    do {
 #pragma unroll
         for (int k = 0; k < N; ++k)
-            if (pending & (1u << k)) {
-                double t;
-                if (ll_load(rows + (size_t)(r0 + k) * LL_ROW + lane, tag, t)) {
-                    v[k] = t;
-                    pending &= ~(1u << k);
-                }
-            }
-    }
+            if ((uint32_t)k < n && !(have_first && k == 0))
+                asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[k]), "=l"(w1[k]) : "l"(p + (size_t)k * LL_ROW));
+        all = true;
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+            if ((uint32_t)k < n && !(have_first && k == 0))
+                all = all && ((w0[k] & 0xffffffff00000000ull) == want) && ((w1[k] & 0xffffffff00000000ull) == want);
+    } while (!all);
     double s = 0.0;
 #pragma unroll
     for (int k = 0; k < N; ++k)
-        if ((uint32_t)k < n) s += v[k];
+        if ((uint32_t)k < n) {
+            const double v = (have_first && k == 0) ? first : __longlong_as_double((long long)((w0[k] & 0xffffffffull) | (w1[k] << 32)));
+            s += v;
+        }
     return s;
 }
 
-// The all-reduce. `v` = this block's row element `lane` (warp 0 calls, all 32 lanes). Block b owns chunk b of the
-// n_chunks chunks of the bucket (blocks with b >= n_chunks contribute nothing but still receive the total).
-// Returns the total of element `lane` in the fixed grouped order.
+// ---- thread-block cluster primitives (PTX) ---------------------------------------------------------------------
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// the same shared-memory variable in block `rank` of this cluster (distributed shared memory)
+__device__ __forceinline__ double dsmem_load_f64(const double* local, uint32_t rank) {
+    const uint32_t l = (uint32_t)__cvta_generic_to_shared(local);
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(l), "r"(rank));
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(r) : "memory");
+    return v;
+}
+
+// The all-reduce WITHOUT clusters. `v` = this block's row element `lane` (warp 0 calls, all 32 lanes). Block b owns
+// chunk b of the n_chunks chunks of the bucket (blocks with b >= n_chunks contribute nothing but still receive the
+// total). Returns the total of element `lane` in the fixed grouped order. Level 1: rows travel through global memory in
+// the flagged format, the group's first block adds them; level 2: it publishes the group row, every block polls the
+// (<= 20) group rows.
 __device__ __forceinline__ double ll_allreduce(const LLView& ll, uint32_t parity, uint32_t tag, uint32_t b, uint32_t n_chunks,
                                                double v, int lane) {
     ulonglong2* crows = ll.chunk_rows + (size_t)parity * LL_MAX_CHUNKS * LL_ROW;
     ulonglong2* grows = ll.group_rows + (size_t)parity * LL_MAX_GROUPS * LL_ROW;
-    if (b < n_chunks) ll_store(crows + (size_t)b * LL_ROW + lane, v, tag);
     const uint32_t n_groups = (n_chunks + LK_GROUP - 1) / LK_GROUP;
-    if (b < n_chunks && (b % LK_GROUP) == 0) {  // leader of group b / LK_GROUP
-        const uint32_t n = min((uint32_t)LK_GROUP, n_chunks - b);
-        double s = 0.0;
-        s += v;  // own row first (chunk b), then the others ascending: the same sequence as ll_sum_rows over all of them
-        if (n > 1) {
-            double r[LK_GROUP - 1];
-            uint32_t pending = (1u << (n - 1)) - 1u;
-            while (pending) {
-#pragma unroll
-                for (int k = 0; k < LK_GROUP - 1; ++k)
-                    if (pending & (1u << k)) {
-                        double t;
-                        if (ll_load(crows + (size_t)(b + 1 + k) * LL_ROW + lane, tag, t)) {
-                            r[k] = t;
-                            pending &= ~(1u << k);
-                        }
-                    }
-            }
-#pragma unroll
-            for (int k = 0; k < LK_GROUP - 1; ++k)
-                if ((uint32_t)k < n - 1) s += r[k];
+    if (b < n_chunks) {
+        if ((b % LK_GROUP) == 0) {
+            const uint32_t n = min((uint32_t)LK_GROUP, n_chunks - b);
+            const double s = ll_sum_rows<LK_GROUP>(crows, b, n, tag, lane, v, true);
+            ll_store(grows + (size_t)(b / LK_GROUP) * LL_ROW + lane, s, tag);
+        } else {
+            ll_store(crows + (size_t)b * LL_ROW + lane, v, tag);
         }
+    }
+    return ll_sum_rows<LL_MAX_GROUPS>(grows, 0, n_groups, tag, lane);
+}
+
+// The cluster's first block (blocks launched as clusters of LK_GROUP = one group per cluster; every block stored its
+// row in its own `xrow` and the cluster passed a cluster barrier): add the group's rows read over distributed shared
+// memory, publish the group row, poll all group rows. Only ONE block per cluster polls global memory — with every
+// block polling, the ~60 cache lines holding the group rows are read by all SMs back to back and the stores everybody
+// waits for queue behind those reads. The caller hands the total to the cluster's other blocks over DSMEM.
+__device__ __forceinline__ double ll_allreduce_cluster_head(const LLView& ll, uint32_t parity, uint32_t tag, uint32_t b,
+                                                            uint32_t n_chunks, double v, int lane, const double* xrow) {
+    ulonglong2* grows = ll.group_rows + (size_t)parity * LL_MAX_GROUPS * LL_ROW;
+    const uint32_t n_groups = (n_chunks + LK_GROUP - 1) / LK_GROUP;
+    if (b < n_chunks) {
+        const uint32_t n = min((uint32_t)LK_GROUP, n_chunks - b);
+        double r[LK_GROUP];
+#pragma unroll
+        for (int k = 1; k < LK_GROUP; ++k) r[k] = ((uint32_t)k < n) ? dsmem_load_f64(xrow + lane, (uint32_t)k) : 0.0;
+        double s = 0.0;
+        s += v;
+#pragma unroll
+        for (int k = 1; k < LK_GROUP; ++k)
+            if ((uint32_t)k < n) s += r[k];
         ll_store(grows + (size_t)(b / LK_GROUP) * LL_ROW + lane, s, tag);
     }
     return ll_sum_rows<LL_MAX_GROUPS>(grows, 0, n_groups, tag, lane);

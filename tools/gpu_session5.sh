@@ -1,0 +1,14 @@
+#!/bin/bash
+cd "$(dirname "$0")/.." && mkdir -p gpurun_out
+timeout -k 10 900 python -m pytest tests/test_gpu_concurrency.py tests/test_gpu_parity.py tests/test_gpu_inputs.py -m gpu -x -q > gpurun_out/s6_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s6_pytest.log
+tail -15 gpurun_out/s6_pytest.log
+timeout -k 10 300 python tools/trace_fused.py leg_fusion_b1 > gpurun_out/s6_trace.log 2>&1; tail -14 gpurun_out/s6_trace.log
+timeout -k 10 300 python tools/trace_fused.py leg_fusion_b1 cluster=0 > gpurun_out/s6_trace_nc.log 2>&1; tail -7 gpurun_out/s6_trace_nc.log
+for v in "cluster=1" "cluster=0" "pdl=0"; do
+  timeout -k 10 300 python bench.py --steps 200 --warmup 20 --no-cpu-baseline --no-batched --param $v > gpurun_out/s6_bench_$(echo $v | tr -d ' =-').json 2> gpurun_out/s6_bench_err.log
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/s6_bench_$(echo $v | tr -d ' =-').json"))
+print("$v", "us/step", d["ms_per_step"]*1e3, "frac", d["roofline"]["frac"], "e2e us", d["e2e"]["us_per_step"], d["e2e"].get("host_phases_us"))
+PY
+done

@@ -9,8 +9,10 @@ name = sys.argv[1] if len(sys.argv) > 1 else "small"
 w = bench.WORKLOADS[name]; ring = 16 if name == "small" else 128
 wl = bench.build_workload(w, 0, ring); cfg = wl["cfg"]
 eng = Engine(cfg); eng.map_build(wl["map_world"], wl["map_body"])
+CL = True
 for kv in sys.argv[2:]:
     k, v = kv.split("="); eng.set_param(k, float(v))
+    if k == "cluster" and float(v) == 0: CL = False
 eng.stage(wl["x0"], abi.init_cov(ring), abi.process_cov_Q(cfg), np.zeros(ring, abi.CLOCK_DTYPE), wl["pts"], wl["offs"], np.zeros(ring))
 for i in range(ring * 2): eng.run_range(i % ring, 1, iters=3)
 eng.sync(); eng.set_param("trace", 1)
@@ -19,6 +21,7 @@ for scan in (3, 4, 5):
     eng.run_range(scan, 1, iters=3); eng.sync()
     tr = np.zeros((1 << 16) * 8, np.uint64); lib().lk_debug_read(eng.h, 2, _p(tr), tr.nbytes)
     nb = int((wl["offs"][scan + 1] - wl["offs"][scan] + 255) // 256)
+    nbg = (nb + 7) // 8 * 8 if CL else nb   # grid (clusters of 8)
     b = tr[:nb * 32].reshape(nb, 32).astype(np.int64); t0 = b[:, 0].min()
     print("scan %d (%d blocks): start spread %.2f, load filter + init %.2f" % (scan, nb, us(b[:, 0].max() - t0), us(np.median(b[:, 1] - b[:, 0]))))
     prev = b[:, 1]
