@@ -111,7 +111,8 @@ struct lk_context {
     uint32_t fused_launches = 0;
     // direct mode of lk_scan_update (one scan, page-locked caller buffers): the kernel reads the points and
     // writes the world cloud / the filter in place, the small inputs ride in the kernel's parameter block
-    int direct_io = 1, inline_in = 1, coop_launch = 0, pdl = 1, use_cluster = 1, n_sms = 148;
+    int direct_io = 1, inline_in = 1, coop_launch = 0, pdl = 1, n_sms = 148, slim_p = 1;
+    size_t h_off_clk = 0;  // offset of the staged clocks inside h_small_in
     int fast_insert = 1;  // update_map: two-launch insert for small buckets, re-projection folded into it
     bool direct = false, direct_ran = false, inline_ok = false;
     const float4* direct_pts = nullptr;
@@ -342,7 +343,7 @@ int lk_set_param(lk_handle h, const char* name, double value) {
     if (!std::strcmp(name, "fast_insert")) { h->fast_insert = (int)value; return LK_OK; }
     if (!std::strcmp(name, "coop_launch")) { h->coop_launch = (int)value; return LK_OK; }
     if (!std::strcmp(name, "pdl")) { h->pdl = (int)value; return LK_OK; }
-    if (!std::strcmp(name, "cluster")) { h->use_cluster = (int)value; return LK_OK; }
+    if (!std::strcmp(name, "slim_p")) { h->slim_p = (int)value; return LK_OK; }
     if (!std::strcmp(name, "direct_io")) { h->direct_io = (int)value; return LK_OK; }
     if (!std::strcmp(name, "inline_in")) { h->inline_in = (int)value; return LK_OK; }
     if (!std::strcmp(name, "trace")) {
@@ -565,6 +566,7 @@ static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P
     std::memcpy(hs + o_x, x, (size_t)batch * sizeof(lk_state));
     std::memcpy(hs + o_P, P, (size_t)batch * 900 * 8);
     std::memcpy(hs + o_clk, clk, (size_t)batch * sizeof(lk_stream_clock));
+    h->h_off_clk = o_clk;
     std::memcpy(hs + o_Q, Q, 900 * 8);
     if (twoTables) {
         std::memcpy(hs + o_chunksL, chunksL.data(), chunksL.size() * sizeof(ChunkDesc));
@@ -715,11 +717,8 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
             max_chunks = std::max(max_chunks, in.chunk_end - in.chunk_begin);
         }
     if (count == 1 && h->use_fused && h->max_chunk_pts <= 256 && !update_map && max_chunks <= (uint32_t)fused_max_blocks(h->device)) {
-        // one scan: the whole bucket loop in ONE persistent kernel, one chunk per block (lk_fused.cu); blocks are
-        // launched as clusters of LK_GROUP when all of them fit on the device at once
-        const uint32_t n_cl = (max_chunks + LK_GROUP - 1) / LK_GROUP;
-        const bool clustered = h->use_cluster && !h->coop_launch && n_cl <= (uint32_t)fused_max_clusters(h->device);
-        const uint32_t grid = clustered ? n_cl * LK_GROUP : max_chunks;
+        // one scan: the whole bucket loop in ONE persistent kernel, one chunk per block (lk_fused.cu)
+        const uint32_t grid = max_chunks;
         FusedArgs fa;
         std::memset(&fa, 0, sizeof(fa));
         fa.pts = h->direct ? h->direct_pts : h->pts.as<float4>();
@@ -765,7 +764,13 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         h->ll_epoch += need;
         fa.iters = iters;
         fa.lane_cache = h->lane_cache;
-        fa.cluster = clustered ? LK_GROUP : 1;
+        {
+            // "no predict": one bucket whose time equals both clocks of the staged filter
+            const lk_stream_clock* ck = reinterpret_cast<const lk_stream_clock*>((const char*)h->h_small_in.p + h->h_off_clk) + first;
+            const StepInit& in0 = h->h_inits[first];
+            fa.slim_p = h->slim_p && h->n_steps == 1 && !mq && in0.active && in0.t_bucket == ck->last_predict_time &&
+                        in0.t_bucket == ck->last_update_time;
+        }
         fa.mv.slots = h->map.slots;
         fa.mv.hash_mask = (uint32_t)(h->map.hash_cap - 1);
         fa.mv.nodes = h->map.nodes;

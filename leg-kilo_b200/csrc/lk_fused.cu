@@ -21,8 +21,6 @@
 // scan's blocks become resident and run their prologue (filter load, point prefetch) while this scan's
 // last blocks drain; everything that could collide with the previous launch (flagged rows, outputs) sits
 // behind griddepcontrol.wait.
-#include <algorithm>
-
 #include "lk_kernels.h"
 #include "lk_obs.cuh"
 #include "lk_pass.cuh"
@@ -54,10 +52,6 @@ struct FusedSmem {
     BlockFilter f;
     ScanConst sc;
     double slice[WARPS * 32];
-    double xrow[2][32];  // this block's row, read by the cluster's first block over DSMEM (by iteration parity)
-    Globals g;           // copies of the parameter-block constants the out-of-line pass reads through pointers
-    MapView mv;
-    double xtot[2][32];  // the total, written by the cluster's first block and read by its peers over DSMEM
     double clk[2];
     union {  // predict and the point passes never overlap in time
         PredictScratch pr;
@@ -65,7 +59,7 @@ struct FusedSmem {
     } u;
 };
 
-static_assert(sizeof(PredictScratch) <= sizeof(((CachedPassSmem<BLOCK>*)0)->tile), "predict scratch must not reach the mbarriers / lane caches");
+static_assert(sizeof(PredictScratch) <= sizeof(((CachedPassSmem<BLOCK>*)0)->tile), "predict scratch must not reach the mbarriers");
 static_assert(sizeof(FusedSmem) <= 227 * 1024, "one block per SM");
 
 // KILO.cc:110-115: covariance with dt since the last UPDATE, state with dt since the last PREDICT; F is built
@@ -125,15 +119,20 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
         const double* cin;
         if constexpr (INL) { Pin = inl.P; xin = inl.x; cin = inl.clk; }
         else { Pin = a.P_in + (size_t)scan * 900; xin = a.x_in + (size_t)scan * 36; cin = reinterpret_cast<const double*>(a.clk_in + scan); }
-        for (int e = tid; e < 900; e += BLOCK) sm->f.P[e] = Pin[e];
+        if (a.slim_p && blockIdx.x != 0) {
+            // a single-bucket scan without a queue never predicts; blocks other than 0 (which stores the covariance) then
+            // only ever read P[:, 0:6]: the 6x6 corner for the solve and the scan constants, the 30x6 strip for delta
+            if (tid < 180) sm->f.P[(tid / 6) * 30 + tid % 6] = Pin[(tid / 6) * 30 + tid % 6];
+        } else {
+            for (int e = tid; e < 900; e += BLOCK) sm->f.P[e] = Pin[e];
+        }
         if (tid < 36) sm->f.x[tid] = xin[tid];
         if (tid < 2) sm->clk[tid] = cin[tid];
     }
-    if (tid < (int)(sizeof(Globals) / 4)) reinterpret_cast<uint32_t*>(&sm->g)[tid] = reinterpret_cast<const uint32_t*>(&a.g)[tid];
-    if (tid == 0) sm->mv = a.mv;
     cached_pass_init<BLOCK>(&sm->u.pass);
     FT(1);
     uint32_t n_eff_total = 0;
+    uint32_t phase = 0;
     uint32_t it_global = 0;
     uint32_t mi = 0;  // next inertial / kinematic sample
     bool dep_waited = false;
@@ -157,45 +156,29 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
         if (tid == 0) sm->clk[0] = in.t_bucket;
         bool updated = false, cov_pending = false;
         uint32_t n_last = 0;
-        sm->u.pass.lc[tid].have = 0;  // per-lane cache state of this bucket (lk_pass.cuh: LaneCache)
+        LaneCache lc;
+        lc.have = 0;
         const bool more_steps = k + 1 < a.n_steps;
         for (int it = 0; it < a.iters; ++it, ++it_global) {
             scan_const_from(&sm->f, &sm->sc);
             __syncthreads();
             // 1) residual rows of my chunk
-            if (!a.lane_cache && sm->u.pass.lc[tid].have == 2) sm->u.pass.lc[tid].have = 1;
-            const double tot = cached_points_pass<BLOCK>(&sm->u.pass, my_count, &sm->sc, &sm->mv, &sm->g, pre.x, pre.y, pre.z);
+            double acc[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+            if (!a.lane_cache && lc.have == 2) lc.have = 1;
+            cached_points_pass<BLOCK>(&sm->u.pass, phase, my_count, sm->sc, a.mv, a.g, acc, lc, pre);
+            const double tot = warp_transpose_sum(acc, lane);
             sm->slice[warp * 32 + lane] = tot;
             __syncthreads();
             FT(2 + it_global * 4);
-            // 2) all-reduce of the block rows, no grid barrier. Clusters: rows meet in the cluster's first block over
-            //    distributed shared memory (cluster barrier 1), that block alone talks to global memory (flagged group
-            //    rows) and hands the total back over DSMEM (cluster barrier 2). No clusters: flagged rows, two levels.
-            const uint32_t par = it_global & 1u;
-            if (a.cluster > 1) {
-                const uint32_t crank = cluster_ctarank();
-                double v = 0.0;
-                if (warp == 0) {
-#pragma unroll
-                    for (int w = 0; w < WARPS; ++w) v += sm->slice[w * 32 + lane];
-                    sm->xrow[par][lane] = v;
-                }
-                cluster_arrive_release();
-                cluster_wait_acquire();
-                if (warp == 0 && crank == 0) {
-                    if (!dep_waited) asm volatile("griddepcontrol.wait;" ::: "memory");  // the rows of the previous launch
-                    const double t = ll_allreduce_cluster_head(a.ll, par, a.epoch + it_global, blockIdx.x, n_chunks, v, lane, sm->xrow[par]);
-                    sm->xtot[par][lane] = t;
-                }
-                cluster_arrive_release();
-                cluster_wait_acquire();
-                if (warp == 0) sm->f.acc[lane] = dsmem_load_f64(&sm->xtot[par][lane], 0);
-            } else if (warp == 0) {
+            // 2) all-reduce of the block rows (warp 0), no barrier
+            if (warp == 0) {
                 double v = 0.0;
 #pragma unroll
                 for (int w = 0; w < WARPS; ++w) v += sm->slice[w * 32 + lane];
                 if (!dep_waited) asm volatile("griddepcontrol.wait;" ::: "memory");  // the rows / outputs of the previous launch
-                sm->f.acc[lane] = ll_allreduce(a.ll, par, a.epoch + it_global, blockIdx.x, n_chunks, v, lane);
+                sm->f.acc[lane] = ll_allreduce(a.ll, it_global & 1u, a.epoch + it_global, blockIdx.x, n_chunks, v, lane);
             }
             dep_waited = true;
             __syncthreads();
@@ -216,7 +199,6 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
         // 4) re-projection with the updated state (KILO.cc:216-224)
         if ((uint32_t)tid < my_count) {
             const double* X = sm->f.x;
-            const LaneCache& lc = sm->u.pass.lc[tid];
             float4 o;
             o.x = (float)(X[0] * lc.pix + X[1] * lc.piy + X[2] * lc.piz + X[9]);
             o.y = (float)(X[3] * lc.pix + X[4] * lc.piy + X[5] * lc.piz + X[10]);
@@ -236,10 +218,6 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
         if (tid == 0) a.n_eff[scan] = n_eff_total;
     }
     FT(31);
-    if (a.cluster > 1) {  // nobody leaves while a peer may still read its shared memory
-        cluster_arrive_release();
-        cluster_wait_acquire();
-    }
 }
 
 template <bool OBS, bool INL>
@@ -266,47 +244,12 @@ cudaError_t launch_one(const FusedArgs& a, const FusedInline* inl, uint32_t grid
     cfg.blockDim = dim3(BLOCK);
     cfg.dynamicSmemBytes = sizeof(FusedSmem);
     cfg.stream = s;
-    cudaLaunchAttribute at[2];
-    int na = 0;
-    if (a.cluster > 1) {
-        at[na].id = cudaLaunchAttributeClusterDimension;
-        at[na].val.clusterDim.x = (unsigned)a.cluster;
-        at[na].val.clusterDim.y = 1;
-        at[na].val.clusterDim.z = 1;
-        ++na;
-    }
-    if (mode == FUSED_LAUNCH_PDL) {
-        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[na].val.programmaticStreamSerializationAllowed = 1;
-        ++na;
-    }
-    cfg.attrs = at;
-    cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, kern, a, *ip);
-}
-
-// clusters of LK_GROUP blocks (one block per SM) that can be resident at once
-template <bool OBS, bool INL>
-int max_clusters_one() {
-    auto kern = k_scan_fused<OBS, INL>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(LK_GROUP * 32);
-    cfg.blockDim = dim3(BLOCK);
-    cfg.dynamicSmemBytes = sizeof(FusedSmem);
     cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = LK_GROUP;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
-    return n;
+    cfg.numAttrs = mode == FUSED_LAUNCH_PDL ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, a, *ip);
 }
 
 }  // namespace
@@ -320,19 +263,6 @@ int fused_max_blocks(int device) {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     int n = sms < LL_MAX_CHUNKS ? sms : LL_MAX_CHUNKS;  // one block per SM (launch bounds + shared memory)
-    if (device >= 0 && device < 64) { cached[device] = n; have[device] = true; }
-    return n;
-}
-
-int fused_max_clusters(int device) {
-    static int cached[64];
-    static bool have[64];
-    if (device >= 0 && device < 64 && have[device]) return cached[device];
-    int n = max_clusters_one<false, false>();
-    n = std::min(n, max_clusters_one<false, true>());
-    n = std::min(n, max_clusters_one<true, false>());
-    n = std::min(n, max_clusters_one<true, true>());
-    n = std::min(n, LL_MAX_GROUPS);
     if (device >= 0 && device < 64) { cached[device] = n; have[device] = true; }
     return n;
 }

@@ -124,7 +124,7 @@ struct FusedArgs {
     uint32_t epoch;  // tag of this launch's first iteration; the launch uses epoch .. epoch + n_steps * iters - 1
     int iters;
     int lane_cache;  // keep per-lane lookups / staged records across the iterations of a bucket
-    int cluster;     // LK_GROUP = launched as thread-block clusters (group rows exchanged over DSMEM), 1 = no clusters
+    int slim_p;        // blocks other than 0 load only P[:, 0:6] (valid when the scan has one bucket, no queue, no predict)
     MapView mv;
     const lk_imu_meas* imu;      // queued samples interleaved with the buckets (exactly one of imu / kin, or none)
     const lk_kinimu_meas* kin;
@@ -137,7 +137,6 @@ struct FusedArgs {
 enum { FUSED_LAUNCH_PLAIN = 0, FUSED_LAUNCH_COOPERATIVE = 1, FUSED_LAUNCH_PDL = 2 };
 size_t fused_smem_bytes();
 int fused_max_blocks(int device);
-int fused_max_clusters(int device);  // resident clusters of LK_GROUP blocks (0 = cluster launch unavailable)
 // inl != null: the filter inputs and the step table ride in the parameter block
 cudaError_t launch_scan_fused(const FusedArgs& a, const FusedInline* inl, uint32_t grid, cudaStream_t s, int mode);
 

@@ -67,25 +67,7 @@ __device__ __forceinline__ double ll_sum_rows(const ulonglong2* rows, uint32_t r
     return s;
 }
 
-// ---- thread-block cluster primitives (PTX) ---------------------------------------------------------------------
-__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-// the same shared-memory variable in block `rank` of this cluster (distributed shared memory)
-__device__ __forceinline__ double dsmem_load_f64(const double* local, uint32_t rank) {
-    const uint32_t l = (uint32_t)__cvta_generic_to_shared(local);
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(l), "r"(rank));
-    double v;
-    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(r) : "memory");
-    return v;
-}
-
-// The all-reduce WITHOUT clusters. `v` = this block's row element `lane` (warp 0 calls, all 32 lanes). Block b owns
+// The all-reduce. `v` = this block's row element `lane` (warp 0 calls, all 32 lanes). Block b owns
 // chunk b of the n_chunks chunks of the bucket (blocks with b >= n_chunks contribute nothing but still receive the
 // total). Returns the total of element `lane` in the fixed grouped order. Level 1: rows travel through global memory in
 // the flagged format, the group's first block adds them; level 2: it publishes the group row, every block polls the
@@ -103,30 +85,6 @@ __device__ __forceinline__ double ll_allreduce(const LLView& ll, uint32_t parity
         } else {
             ll_store(crows + (size_t)b * LL_ROW + lane, v, tag);
         }
-    }
-    return ll_sum_rows<LL_MAX_GROUPS>(grows, 0, n_groups, tag, lane);
-}
-
-// The cluster's first block (blocks launched as clusters of LK_GROUP = one group per cluster; every block stored its
-// row in its own `xrow` and the cluster passed a cluster barrier): add the group's rows read over distributed shared
-// memory, publish the group row, poll all group rows. Only ONE block per cluster polls global memory — with every
-// block polling, the ~60 cache lines holding the group rows are read by all SMs back to back and the stores everybody
-// waits for queue behind those reads. The caller hands the total to the cluster's other blocks over DSMEM.
-__device__ __forceinline__ double ll_allreduce_cluster_head(const LLView& ll, uint32_t parity, uint32_t tag, uint32_t b,
-                                                            uint32_t n_chunks, double v, int lane, const double* xrow) {
-    ulonglong2* grows = ll.group_rows + (size_t)parity * LL_MAX_GROUPS * LL_ROW;
-    const uint32_t n_groups = (n_chunks + LK_GROUP - 1) / LK_GROUP;
-    if (b < n_chunks) {
-        const uint32_t n = min((uint32_t)LK_GROUP, n_chunks - b);
-        double r[LK_GROUP];
-#pragma unroll
-        for (int k = 1; k < LK_GROUP; ++k) r[k] = ((uint32_t)k < n) ? dsmem_load_f64(xrow + lane, (uint32_t)k) : 0.0;
-        double s = 0.0;
-        s += v;
-#pragma unroll
-        for (int k = 1; k < LK_GROUP; ++k)
-            if ((uint32_t)k < n) s += r[k];
-        ll_store(grows + (size_t)(b / LK_GROUP) * LL_ROW + lane, s, tag);
     }
     return ll_sum_rows<LL_MAX_GROUPS>(grows, 0, n_groups, tag, lane);
 }

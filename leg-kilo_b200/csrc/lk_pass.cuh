@@ -38,6 +38,27 @@ struct DebugRows {  // lk_debug_residuals outputs (nullable)
     int32_t* key;
 };
 
+__device__ __forceinline__ void plane_from_smem(const unsigned char* slot, PlaneRec& r) {
+    const double2* q = reinterpret_cast<const double2*>(slot);
+    double2 v[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) v[i] = q[i];
+    r.c[0] = v[0].x; r.c[1] = v[0].y; r.c[2] = v[1].x;
+    r.n[0] = v[1].y; r.n[1] = v[2].x; r.n[2] = v[2].y;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        r.pv[2 * i] = v[3 + i].x;
+        r.pv[2 * i + 1] = v[3 + i].y;
+    }
+    r.pv[20] = v[13].x;
+    long long dr = __double_as_longlong(v[13].y);
+    r.d = __int_as_float((int)(dr & 0xffffffffll));
+    r.radius = __int_as_float((int)(dr >> 32));
+    long long fc = __double_as_longlong(v[14].x);
+    r.flags = (uint32_t)(fc & 0xffffffffll);
+    r.child_base = (int)(fc >> 32);
+}
+
 __device__ __forceinline__ void accumulate_row(const Row& row, double (&acc)[32]) {
     const double w = 1.0 / row.R;
     int q = 0;
@@ -163,6 +184,15 @@ __device__ __forceinline__ bool fallback_pick(const PS* ps, uint32_t& fb_slot) {
     return threadIdx.x < n_fb;
 }
 
+__device__ __forceinline__ bool eval_record(const MapNode* __restrict__ nodes, const PlaneRec& r, const PointCtx& pc,
+                                            const ScanConst& sc, const Globals& g, Row& row) {
+    double prob = 0.0;
+    if (r.flags & LK_NODE_IS_PLANE) return eval_plane(r, pc, sc, g, false, prob, row);
+    const uint32_t cmask = (r.flags >> LK_NODE_CHILDMASK_SHIFT) & 0xffu;
+    if (g.max_layer >= 1 && r.child_base >= 0 && cmask) return visit_subtree(nodes, r.child_base, cmask, &pc, &sc, &g, &prob, &row);
+    return false;
+}
+
 // One pass, every point looked up afresh (multi-kernel path). `phase` is the warp's mbarrier parity (start at 0,
 // carried between passes). base_idx = absolute index of pts[0] (debug output addressing).
 template <int NTHREADS, bool DEBUG>
@@ -205,7 +235,9 @@ __device__ __forceinline__ void block_points_pass(PassSmem<NTHREADS>* ps, uint32
     Row row;
     bool ok = false;
     if (root >= 0) {
-        ok = eval_record(mv.nodes, my_slot, pc, sc, g, row);
+        PlaneRec r;
+        plane_from_smem(my_slot, r);
+        ok = eval_record(mv.nodes, r, pc, sc, g, row);
     }
     fallback_list<NTHREADS>(ps, root >= 0 && !ok && near >= 0, pc, near, lane, warp);
     if (DEBUG) {
@@ -228,7 +260,9 @@ __device__ __forceinline__ void block_points_pass(PassSmem<NTHREADS>* ps, uint32
         PointCtx fc;
         fc.pbx = f.pc[0]; fc.pby = f.pc[1]; fc.pbz = f.pc[2]; fc.pix = f.pc[3]; fc.piy = f.pc[4]; fc.piz = f.pc[5];
         fc.pwx = f.pc[6]; fc.pwy = f.pc[7]; fc.pwz = f.pc[8]; fc.r2 = f.pc[9]; fc.range2 = f.pc[10];
-        ok2 = eval_record(mv.nodes, mv.nodes + f.near, fc, sc, g, row2);
+        PlaneRec r;
+        load_plane(mv.nodes + f.near, r);
+        ok2 = eval_record(mv.nodes, r, fc, sc, g, row2);
         if (ok2 && DEBUG) {
             const size_t gi = base_idx + f.idx;
             dbg.ok[gi] = 1;
@@ -253,11 +287,10 @@ __device__ __forceinline__ void block_points_pass(PassSmem<NTHREADS>* ps, uint32
 // the fallback round reads its record from shared memory instead of paying another dependent global round trip.
 // Arithmetic and accumulation order are those of block_points_pass (bitwise-equal sums).
 // =================================================================================================
-struct LaneCache {  // lives in shared memory (one per thread), not in registers: the kernel is register-bound
+struct LaneCache {
     double pbx, pby, pbz, pix, piy, piz, r2, range2;
     int kx, ky, kz, nx, ny, nz, root, near;
     int have;  // 0 = nothing cached, 1 = point quantities cached, 2 = + keys / root / near / staged records
-    int pad;
 };
 
 template <int NTHREADS>
@@ -270,55 +303,27 @@ struct CachedPassSmem {
     } fb[NTHREADS];
     uint64_t bar[NTHREADS / 32];
     uint32_t wcnt[NTHREADS / 32];
-    uint32_t phase[NTHREADS / 32];  // mbarrier parity of every warp
-    LaneCache lc[NTHREADS];
 };
 
 template <int NTHREADS>
 __device__ __forceinline__ void cached_pass_init(CachedPassSmem<NTHREADS>* ps) {
     const int tid = threadIdx.x;
-    if ((tid & 31) == 0) {
-        mbar_init(&ps->bar[tid >> 5], 1);
-        ps->phase[tid >> 5] = 0;
-    }
+    if ((tid & 31) == 0) mbar_init(&ps->bar[tid >> 5], 1);
     mbar_init_fence();
     __syncthreads();
 }
 
-// The fallback round of the cached pass, out of line: in most passes no warp has an entry and the call is skipped
-// altogether; when it runs, it has the whole register file to itself instead of squeezing into the caller's.
 template <int NTHREADS>
-__device__ __noinline__ bool cached_fallback_eval(const CachedPassSmem<NTHREADS>* ps, uint32_t fb_slot, const MapNode* nodes,
-                                                  const ScanConst* scp, const Globals* gp, Row* out) {
-    const typename CachedPassSmem<NTHREADS>::Fallback& f = ps->fb[fb_slot];
-    PointCtx fc;
-    fc.pbx = f.pc[0]; fc.pby = f.pc[1]; fc.pbz = f.pc[2]; fc.pix = f.pc[3]; fc.piy = f.pc[4]; fc.piz = f.pc[5];
-    fc.pwx = f.pc[6]; fc.pwy = f.pc[7]; fc.pwz = f.pc[8]; fc.r2 = f.pc[9]; fc.range2 = f.pc[10];
-    Row row;
-    const bool ok = eval_record(nodes, ps->tile[1] + (size_t)f.idx * TILE_STRIDE, fc, *scp, *gp, row);
-    if (ok) *out = row;
-    return ok;
-}
-
-// Out of line on purpose: its register allocation then starts from a clean slate instead of competing with everything
-// the persistent kernel keeps alive. Returns, for lane L, the sum over the warp's rows of accumulator L (A upper 21 |
-// b 6 | sum R | count), i.e. warp_transpose_sum of the per-lane accumulators. `pre` = this lane's point (read once).
-template <int NTHREADS>
-__device__ __noinline__ double cached_points_pass(CachedPassSmem<NTHREADS>* ps, uint32_t count, const ScanConst* scp,
-                                                  const MapView* mvp, const Globals* gp, float pre_x, float pre_y, float pre_z) {
-    const ScanConst& sc = *scp;
-    const MapView mv = *mvp;
-    const Globals& g = *gp;
-    LaneCache& lc = ps->lc[threadIdx.x];
-    int have = lc.have;
-    const float4 pre = make_float4(pre_x, pre_y, pre_z, 0.f);
+__device__ __forceinline__ void cached_points_pass(CachedPassSmem<NTHREADS>* ps, uint32_t& phase, uint32_t count,
+                                                   const ScanConst& sc, const MapView& mv, const Globals& g,
+                                                   double (&acc)[32], LaneCache& lc, float4 pre) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool active = (uint32_t)tid < count;
     PointCtx pc;
     int root = -1, near = -1;
     bool gather_home = false, gather_near = false;
     if (active) {
-        if (have == 0) {
+        if (lc.have == 0) {
             const double bx = (double)pre.x, by = (double)pre.y, bz = (double)pre.z;
             lc.pix = g.Re[0] * bx + g.Re[1] * by + g.Re[2] * bz + g.te[0];
             lc.piy = g.Re[3] * bx + g.Re[4] * by + g.Re[5] * bz + g.te[1];
@@ -328,7 +333,7 @@ __device__ __noinline__ double cached_points_pass(CachedPassSmem<NTHREADS>* ps, 
             lc.r2 = lc.pbx * lc.pbx + lc.pby * lc.pby + lc.pbz * lc.pbz;
             const float range = (float)sqrt(lc.r2);
             lc.range2 = (double)range * (double)range;
-            have = 1;
+            lc.have = 1;
         }
         pc.pbx = lc.pbx; pc.pby = lc.pby; pc.pbz = lc.pbz; pc.pix = lc.pix; pc.piy = lc.piy; pc.piz = lc.piz;
         pc.r2 = lc.r2; pc.range2 = lc.range2;
@@ -341,7 +346,7 @@ __device__ __noinline__ double cached_points_pass(CachedPassSmem<NTHREADS>* ps, 
         int nx, ny, nz;
         neighbour_key(g, lx, ly, lz, kx, ky, kz, nx, ny, nz);
         const bool differs = (nx != kx) || (ny != ky) || (nz != kz);
-        const bool same_home = have == 2 && lc.kx == kx && lc.ky == ky && lc.kz == kz;
+        const bool same_home = lc.have == 2 && lc.kx == kx && lc.ky == ky && lc.kz == kz;
         if (same_home) {
             root = lc.root;
             near = lc.near;
@@ -374,16 +379,16 @@ __device__ __noinline__ double cached_points_pass(CachedPassSmem<NTHREADS>* ps, 
         __syncwarp();
         if (gather_home) bulk_g2s(home_slot, mv.nodes + root, 256u, &ps->bar[warp]);
         if (gather_near) bulk_g2s(near_slot, mv.nodes + near, 256u, &ps->bar[warp]);
-        const uint32_t phase = ps->phase[warp];
         mbar_wait(&ps->bar[warp], phase);
-        __syncwarp();
-        if (lane == 0) ps->phase[warp] = phase ^ 1u;
+        phase ^= 1u;
     }
     // ---- gates + row -----------------------------------------------------------------------------
     Row row;
     bool ok = false;
     if (root >= 0) {
-        ok = eval_record(mv.nodes, home_slot, pc, sc, g, row);
+        PlaneRec r;
+        plane_from_smem(home_slot, r);
+        ok = eval_record(mv.nodes, r, pc, sc, g, row);
     }
     fallback_list<NTHREADS>(ps, root >= 0 && !ok && near >= 0, pc, near, lane, warp);
     __syncthreads();
@@ -391,16 +396,152 @@ __device__ __noinline__ double cached_points_pass(CachedPassSmem<NTHREADS>* ps, 
     uint32_t fb_slot = 0;
     Row row2;
     bool ok2 = false;
-    if (fallback_pick<NTHREADS>(ps, fb_slot)) ok2 = cached_fallback_eval<NTHREADS>(ps, fb_slot, mv.nodes, &sc, &g, &row2);
-    // the accumulator is born only now: nothing of it is live across the evaluations (and the out-of-line calls)
-    double acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+    if (fallback_pick<NTHREADS>(ps, fb_slot)) {
+        const typename CachedPassSmem<NTHREADS>::Fallback& f = ps->fb[fb_slot];
+        PointCtx fc;
+        fc.pbx = f.pc[0]; fc.pby = f.pc[1]; fc.pbz = f.pc[2]; fc.pix = f.pc[3]; fc.piy = f.pc[4]; fc.piz = f.pc[5];
+        fc.pwx = f.pc[6]; fc.pwy = f.pc[7]; fc.pwz = f.pc[8]; fc.r2 = f.pc[9]; fc.range2 = f.pc[10];
+        PlaneRec r;
+        plane_from_smem(ps->tile[1] + (size_t)f.idx * TILE_STRIDE, r);
+        ok2 = eval_record(mv.nodes, r, fc, sc, g, row2);
+    }
     if (ok) accumulate_row(row, acc);
     if (ok2) accumulate_row(row2, acc);
     __syncthreads();  // the fallback list is rewritten by the next pass
-    return warp_transpose_sum(acc, lane);
 }
 
+
+// =================================================================================================
+// Throughput variant: every warp streams its own 32-point groups of the block's chunk with no
+// block-wide barrier inside the loop; records are staged by warp-cooperative 16-byte async copies
+// (two 256-byte records per warp instruction: 4 cache lines instead of 32); points that fail at
+// home only remember their neighbour key and are finished in bulk after the loop.
+// =================================================================================================
+template <int NTHREADS, int MAXPTS>
+struct StreamSmem {
+    __align__(16) unsigned char tile[NTHREADS * TILE_STRIDE];  // 32 slots per warp
+    struct Fallback {
+        uint32_t idx;
+    } fb[MAXPTS];
+    uint32_t n_fb;
+    uint32_t pad[3];
+};
+
+__device__ __forceinline__ bool eval_node(const MapView& mv, const PlaneRec& r, const PointCtx& pc, const ScanConst& sc,
+                                          const Globals& g, Row& row) {
+    double prob = 0.0;
+    if (r.flags & LK_NODE_IS_PLANE) return eval_plane(r, pc, sc, g, false, prob, row);
+    const uint32_t cmask = (r.flags >> LK_NODE_CHILDMASK_SHIFT) & 0xffu;
+    if (g.max_layer >= 1 && r.child_base >= 0 && cmask) return visit_subtree(mv.nodes, r.child_base, cmask, &pc, &sc, &g, &prob, &row);
+    return false;
+}
+
+// eval_plane reading the staged record field by field (no 29-double register image): centre and
+// normal first, the cheap float gate, and only then the 21 plane-covariance terms.
+__device__ __forceinline__ bool eval_plane_staged(const unsigned char* slot, const PointCtx& pc, const ScanConst& sc,
+                                                  const Globals& g, Row& row) {
+    const double* q = reinterpret_cast<const double*>(slot);
+    const double2 v0 = *reinterpret_cast<const double2*>(q), v1 = *reinterpret_cast<const double2*>(q + 2),
+                  v2 = *reinterpret_cast<const double2*>(q + 4);
+    const double c0 = v0.x, c1 = v0.y, c2 = v1.x, n0 = v1.y, n1 = v2.x, n2 = v2.y;
+    const float2 dr = *reinterpret_cast<const float2*>(q + 27);
+    const double s = n0 * pc.pwx + n1 * pc.pwy + n2 * pc.pwz + (double)dr.x;
+    const float dis = (float)fabs(s);
+    const double ax = pc.pwx - c0, ay = pc.pwy - c1, az = pc.pwz - c2;
+    const float dc = (float)(ax * ax + ay * ay + az * az);
+    const float rd = sqrtf(__fsub_rn(dc, __fmul_rn(dis, dis)));
+    if (!((double)rd <= 3.0 * (double)dr.y)) return false;
+    const double J0 = ax, J1 = ay, J2 = az, J3 = -n0, J4 = -n1, J5 = -n2;
+    const double* pv = q + 6;
+    double sigma_pl = J0 * (pv[0] * J0 + 2.0 * (pv[1] * J1 + pv[2] * J2 + pv[3] * J3 + pv[4] * J4 + pv[5] * J5));
+    sigma_pl += J1 * (pv[6] * J1 + 2.0 * (pv[7] * J2 + pv[8] * J3 + pv[9] * J4 + pv[10] * J5));
+    sigma_pl += J2 * (pv[11] * J2 + 2.0 * (pv[12] * J3 + pv[13] * J4 + pv[14] * J5));
+    sigma_pl += J3 * (pv[15] * J3 + 2.0 * (pv[16] * J4 + pv[17] * J5));
+    sigma_pl += J4 * (pv[18] * J4 + 2.0 * (pv[19] * J5));
+    sigma_pl += J5 * (pv[20] * J5);
+    const double qx = sc.R[0] * n0 + sc.R[3] * n1 + sc.R[6] * n2;
+    const double qy = sc.R[1] * n0 + sc.R[4] * n1 + sc.R[7] * n2;
+    const double qz = sc.R[2] * n0 + sc.R[5] * n1 + sc.R[8] * n2;
+    const double hx = pc.piy * qz - pc.piz * qy, hy = pc.piz * qx - pc.pix * qz, hz = pc.pix * qy - pc.piy * qx;
+    const double wx = g.Re[0] * qx + g.Re[3] * qy + g.Re[6] * qz;
+    const double wy = g.Re[1] * qx + g.Re[4] * qy + g.Re[7] * qz;
+    const double wz = g.Re[2] * qx + g.Re[5] * qy + g.Re[8] * qz;
+    const double uw = pc.pbx * wx + pc.pby * wy + pc.pbz * wz;
+    const double ww = wx * wx + wy * wy + wz * wz;
+    const double uw2 = uw * uw / pc.r2;
+    const double body = (double)g.rv * uw2 + pc.range2 * g.dv * (ww - uw2);
+    const double state = quad_sym3(sc.Pth, hx, hy, hz) + quad_sym3(sc.Ppp, n0, n1, n2);
+    const double sigma_l = sigma_pl + body + state;
+    const double lhs = (double)dis * (double)dis;
+    const double rhs = g.sigma_num * g.sigma_num * sigma_l;
+    bool pass;
+    if (lhs < rhs * (1.0 - 1e-12)) pass = true;
+    else if (lhs > rhs * (1.0 + 1e-12)) pass = false;
+    else pass = (double)dis < g.sigma_num * sqrt(sigma_l);
+    if (!pass) return false;
+    row.h[0] = hx; row.h[1] = hy; row.h[2] = hz; row.h[3] = n0; row.h[4] = n1; row.h[5] = n2;
+    row.z = -(double)(float)s;
+    row.R = g.ratio * (sigma_pl + body);
+    return true;
+}
+
+template <int NTHREADS, int MAXPTS>
+__device__ __forceinline__ void block_points_stream(StreamSmem<NTHREADS, MAXPTS>* ss, const float4* __restrict__ pts,
+                                                    uint32_t count, const ScanConst& sc, const MapView& mv, const Globals& g,
+                                                    double (&acc)[32]) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NTHREADS / 32;
+    unsigned char* wtile = ss->tile + (size_t)warp * 32 * TILE_STRIDE;
+    const int half = lane >> 4, sub = lane & 15;
+    float4 pt_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp * 32 + lane < count) pt_next = __ldg(pts + warp * 32 + lane);
+    for (uint32_t g0 = warp * 32; g0 < count; g0 += NW * 32) {
+        const uint32_t i = g0 + lane;
+        const bool active = i < count;
+        const float4 pt = pt_next;
+        if (i + NW * 32 < count) pt_next = __ldg(pts + i + NW * 32);  // next group's point: off the critical path
+        PointCtx pc;
+        float lx = 0, ly = 0, lz = 0;
+        int kx = 0, ky = 0, kz = 0, root = -1;
+        if (active) {
+            prepare_point(pt, sc, g, pc, lx, ly, lz);
+            kx = (int)lx; ky = (int)ly; kz = (int)lz;
+            const uint32_t ih = hash_key(kx, ky, kz) & mv.hash_mask;
+            root = resolve_pair(mv.slots, mv.hash_mask, ih, load_pair(mv.slots, ih), kx, ky, kz);
+        }
+        // cooperative gather: instruction j moves records of lanes 2j and 2j+1 (16 lanes x 16 B each)
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int r = __shfl_sync(0xffffffffu, root, 2 * j + half);
+            if (r >= 0) cp_async16(wtile + (size_t)(2 * j + half) * TILE_STRIDE + sub * 16,
+                                   reinterpret_cast<const unsigned char*>(mv.nodes + r) + sub * 16);
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        if (root >= 0) {
+            const unsigned char* slot = wtile + (size_t)lane * TILE_STRIDE;
+            const uint32_t flags = *reinterpret_cast<const uint32_t*>(slot + 224);
+            Row row;
+            if ((flags & LK_NODE_IS_PLANE) && eval_plane_staged(slot, pc, sc, g, row)) {
+                accumulate_row(row, acc);
+            } else {
+                // not a plane here, or gated out: the point is finished in bulk with the full reference
+                // sequence (home octree descent, then the ONE neighbour voxel of KILO.cc:156-178)
+                const uint32_t e = atomicAdd(&ss->n_fb, 1u);
+                ss->fb[e].idx = i;
+            }
+        }
+        __syncwarp();  // the tile is rewritten by the next group
+    }
+    __syncthreads();
+    const uint32_t n_fb = ss->n_fb;
+    for (uint32_t e = tid; e < n_fb; e += NTHREADS) {
+        Row row;
+        if (point_row(__ldg(pts + ss->fb[e].idx), sc, mv, g, row, nullptr)) accumulate_row(row, acc);
+    }
+    __syncthreads();
+    if (tid == 0) ss->n_fb = 0;
+}
 
 }  // namespace lk

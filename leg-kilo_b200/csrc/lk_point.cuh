@@ -12,11 +12,34 @@
 
 namespace lk {
 
-// The 232 bytes of a plane record (lk_map_node) the path reads, addressed in place — in shared memory where a record was
-// staged, in global memory on the rare paths: centre 3 | normal 3 | Sigma_plane upper triangle 21 doubles, then
-// {d, radius} as floats (double index 27), flags (byte 224), child_base (byte 228).
-__device__ __forceinline__ uint32_t rec_flags(const void* rec) { return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(rec) + 224); }
-__device__ __forceinline__ int rec_child_base(const void* rec) { return *reinterpret_cast<const int*>(reinterpret_cast<const char*>(rec) + 228); }
+struct PlaneRec {
+    double c[3], n[3], pv[21];
+    float d, radius;
+    uint32_t flags;
+    int child_base;
+};
+
+// 15 x 128-bit read-only loads cover the 232 bytes the path needs (lk_map_node).
+__device__ __forceinline__ void load_plane(const MapNode* __restrict__ nd, PlaneRec& r) {
+    const double2* q = reinterpret_cast<const double2*>(nd);
+    double2 v[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) v[i] = __ldg(q + i);
+    r.c[0] = v[0].x; r.c[1] = v[0].y; r.c[2] = v[1].x;
+    r.n[0] = v[1].y; r.n[1] = v[2].x; r.n[2] = v[2].y;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        r.pv[2 * i] = v[3 + i].x;
+        r.pv[2 * i + 1] = v[3 + i].y;
+    }
+    r.pv[20] = v[13].x;
+    long long dr = __double_as_longlong(v[13].y);
+    r.d = __int_as_float((int)(dr & 0xffffffffll));
+    r.radius = __int_as_float((int)(dr >> 32));
+    long long fc = __double_as_longlong(v[14].x);
+    r.flags = (uint32_t)(fc & 0xffffffffll);
+    r.child_base = (int)(fc >> 32);
+}
 
 struct PointCtx {
     double pbx, pby, pbz;  // lidar-frame point as calcBodyCov sees it (z == 0 -> 1e-4)
@@ -36,60 +59,60 @@ __device__ __forceinline__ double quad_sym3(const double* S, double a, double b,
     return S[0] * a * a + S[3] * b * b + S[5] * c * c + 2.0 * (S[1] * a * b + S[2] * a * c + S[4] * b * c);
 }
 
-// build_single_residual's plane branch (voxel_map.cc:370-411) + the row of KILO.cc:192-209, reading the record field
-// by field (no 29-double register image): centre and normal first, the cheap float gate, and only then the 21
-// plane-covariance terms. ONE evaluation for every path (latency and throughput families), so that they differ only in
-// the order of their sums.
-__device__ __forceinline__ bool eval_plane_at(const double* __restrict__ q, const PointCtx& pc, const ScanConst& sc,
-                                              const Globals& g, bool need_prob, double& prob, Row& row) {
-    const double2 v0 = *reinterpret_cast<const double2*>(q), v1 = *reinterpret_cast<const double2*>(q + 2),
-                  v2 = *reinterpret_cast<const double2*>(q + 4);
-    const double c0 = v0.x, c1 = v0.y, c2 = v1.x, n0 = v1.y, n1 = v2.x, n2 = v2.y;
-    const float2 dr = *reinterpret_cast<const float2*>(q + 27);  // {d, radius}: floats in the reference (voxel_map.h:103,107)
-    const double s = n0 * pc.pwx + n1 * pc.pwy + n2 * pc.pwz + (double)dr.x;
-    const float dis = (float)fabs(s);
-    const double ax = pc.pwx - c0, ay = pc.pwy - c1, az = pc.pwz - c2;
-    const float dc = (float)(ax * ax + ay * ay + az * az);
-    const float rd = sqrtf(__fsub_rn(dc, __fmul_rn(dis, dis)));  // float arithmetic as in the reference
-    if (!((double)rd <= 3.0 * (double)dr.y)) return false;
+// build_single_residual's plane branch (voxel_map.cc:370-411) + the row of KILO.cc:192-209.
+__device__ __forceinline__ bool eval_plane(const PlaneRec& r, const PointCtx& pc, const ScanConst& sc,
+                                           const Globals& g, bool need_prob, double& prob, Row& row) {
+    double s = r.n[0] * pc.pwx + r.n[1] * pc.pwy + r.n[2] * pc.pwz + (double)r.d;
+    float dis = (float)fabs(s);
+    double ax = pc.pwx - r.c[0], ay = pc.pwy - r.c[1], az = pc.pwz - r.c[2];
+    float dc = (float)(ax * ax + ay * ay + az * az);
+    float rd = sqrtf(__fsub_rn(dc, __fmul_rn(dis, dis)));  // float arithmetic as in the reference
+    if (!((double)rd <= 3.0 * (double)r.radius)) return false;
+
     // J_nq Sigma_plane J_nq^T, J_nq = [(pw - c)^T, -n^T]
-    const double J0 = ax, J1 = ay, J2 = az, J3 = -n0, J4 = -n1, J5 = -n2;
-    const double* pv = q + 6;
-    double sigma_pl = J0 * (pv[0] * J0 + 2.0 * (pv[1] * J1 + pv[2] * J2 + pv[3] * J3 + pv[4] * J4 + pv[5] * J5));
-    sigma_pl += J1 * (pv[6] * J1 + 2.0 * (pv[7] * J2 + pv[8] * J3 + pv[9] * J4 + pv[10] * J5));
-    sigma_pl += J2 * (pv[11] * J2 + 2.0 * (pv[12] * J3 + pv[13] * J4 + pv[14] * J5));
-    sigma_pl += J3 * (pv[15] * J3 + 2.0 * (pv[16] * J4 + pv[17] * J5));
-    sigma_pl += J4 * (pv[18] * J4 + 2.0 * (pv[19] * J5));
-    sigma_pl += J5 * (pv[20] * J5);
+    const double J0 = ax, J1 = ay, J2 = az, J3 = -r.n[0], J4 = -r.n[1], J5 = -r.n[2];
+    const double* pv = r.pv;
+    double t0 = pv[0] * J0 + 2.0 * (pv[1] * J1 + pv[2] * J2 + pv[3] * J3 + pv[4] * J4 + pv[5] * J5);
+    double t1 = pv[6] * J1 + 2.0 * (pv[7] * J2 + pv[8] * J3 + pv[9] * J4 + pv[10] * J5);
+    double t2 = pv[11] * J2 + 2.0 * (pv[12] * J3 + pv[13] * J4 + pv[14] * J5);
+    double t3 = pv[15] * J3 + 2.0 * (pv[16] * J4 + pv[17] * J5);
+    double t4 = pv[18] * J4 + 2.0 * (pv[19] * J5);
+    double t5 = pv[20] * J5;
+    double sigma_pl = J0 * t0 + J1 * t1 + J2 * t2 + J3 * t3 + J4 * t4 + J5 * t5;
+
     // q = R^T n ; h_theta = pi x q ; w = (R Re)^T n = Re^T q
-    const double qx = sc.R[0] * n0 + sc.R[3] * n1 + sc.R[6] * n2;
-    const double qy = sc.R[1] * n0 + sc.R[4] * n1 + sc.R[7] * n2;
-    const double qz = sc.R[2] * n0 + sc.R[5] * n1 + sc.R[8] * n2;
-    const double hx = pc.piy * qz - pc.piz * qy, hy = pc.piz * qx - pc.pix * qz, hz = pc.pix * qy - pc.piy * qx;
-    const double wx = g.Re[0] * qx + g.Re[3] * qy + g.Re[6] * qz;
-    const double wy = g.Re[1] * qx + g.Re[4] * qy + g.Re[7] * qz;
-    const double wz = g.Re[2] * qx + g.Re[5] * qy + g.Re[8] * qz;
-    const double uw = pc.pbx * wx + pc.pby * wy + pc.pbz * wz;
-    const double ww = wx * wx + wy * wy + wz * wz;
-    const double uw2 = uw * uw / pc.r2;  // (u.w)^2
-    const double body = (double)g.rv * uw2 + pc.range2 * g.dv * (ww - uw2);
-    const double state = quad_sym3(sc.Pth, hx, hy, hz) + quad_sym3(sc.Ppp, n0, n1, n2);
-    const double sigma_l = sigma_pl + body + state;
+    double qx = sc.R[0] * r.n[0] + sc.R[3] * r.n[1] + sc.R[6] * r.n[2];
+    double qy = sc.R[1] * r.n[0] + sc.R[4] * r.n[1] + sc.R[7] * r.n[2];
+    double qz = sc.R[2] * r.n[0] + sc.R[5] * r.n[1] + sc.R[8] * r.n[2];
+    double hx = pc.piy * qz - pc.piz * qy;
+    double hy = pc.piz * qx - pc.pix * qz;
+    double hz = pc.pix * qy - pc.piy * qx;
+    double wx = g.Re[0] * qx + g.Re[3] * qy + g.Re[6] * qz;
+    double wy = g.Re[1] * qx + g.Re[4] * qy + g.Re[7] * qz;
+    double wz = g.Re[2] * qx + g.Re[5] * qy + g.Re[8] * qz;
+    double uw = pc.pbx * wx + pc.pby * wy + pc.pbz * wz;
+    double ww = wx * wx + wy * wy + wz * wz;
+    double uw2 = uw * uw / pc.r2;  // (u.w)^2
+    double body = (double)g.rv * uw2 + pc.range2 * g.dv * (ww - uw2);
+    double state = quad_sym3(sc.Pth, hx, hy, hz) + quad_sym3(sc.Ppp, r.n[0], r.n[1], r.n[2]);
+    double sigma_l = sigma_pl + body + state;
+
     // gate 2: dis_to_plane < sigma_num * sqrt(sigma_l)   (voxel_map.cc:387), squared with an exact
     // fallback at the boundary so the decision equals the reference's comparison.
-    const double lhs = (double)dis * (double)dis;
-    const double rhs = g.sigma_num * g.sigma_num * sigma_l;
+    double lhs = (double)dis * (double)dis;
+    double rhs = g.sigma_num * g.sigma_num * sigma_l;
     bool pass;
     if (lhs < rhs * (1.0 - 1e-12)) pass = true;
     else if (lhs > rhs * (1.0 + 1e-12)) pass = false;
     else pass = (double)dis < g.sigma_num * sqrt(sigma_l);
     if (!pass) return false;
     if (need_prob) {
-        const double this_prob = 1.0 / sqrt(sigma_l) * exp(-0.5 * (double)dis * (double)dis / sigma_l);
+        double this_prob = 1.0 / sqrt(sigma_l) * exp(-0.5 * (double)dis * (double)dis / sigma_l);
         if (!(this_prob > prob)) return true;  // is_success without replacing the candidate
         prob = this_prob;
     }
-    row.h[0] = hx; row.h[1] = hy; row.h[2] = hz; row.h[3] = n0; row.h[4] = n1; row.h[5] = n2;
+    row.h[0] = hx; row.h[1] = hy; row.h[2] = hz;
+    row.h[3] = r.n[0]; row.h[4] = r.n[1]; row.h[5] = r.n[2];
     row.z = -(double)(float)s;  // dis_to_plane_ is float (voxel_map.h:92)
     row.R = g.ratio * (sigma_pl + body);
     return true;
@@ -128,15 +151,14 @@ static __device__ __noinline__ bool visit_subtree(const MapNode* __restrict__ no
         int c = __ffs(m) - 1;  // child order 0..7 as the reference's loop
         st_mask[sp - 1] = m & (m - 1);
         int layer = sp;  // children of a layer-(sp-1) node
-        const MapNode* cn = nodes + st_base[sp - 1] + c;
-        const uint32_t cflags = rec_flags(cn);
-        if (cflags & LK_NODE_IS_PLANE) {
-            if (eval_plane_at(reinterpret_cast<const double*>(cn), pc, sc, g, true, prob, row)) ok = true;
+        PlaneRec cr;
+        load_plane(nodes + st_base[sp - 1] + c, cr);
+        if (cr.flags & LK_NODE_IS_PLANE) {
+            if (eval_plane(cr, pc, sc, g, true, prob, row)) ok = true;
         } else if (layer < g.max_layer && sp < 4) {
-            const uint32_t cm = (cflags >> LK_NODE_CHILDMASK_SHIFT) & 0xffu;
-            const int cb = rec_child_base(cn);
-            if (cb >= 0 && cm) {
-                st_base[sp] = cb;
+            uint32_t cm = (cr.flags >> LK_NODE_CHILDMASK_SHIFT) & 0xffu;
+            if (cr.child_base >= 0 && cm) {
+                st_base[sp] = cr.child_base;
                 st_mask[sp] = cm;
                 ++sp;
             }
@@ -145,22 +167,6 @@ static __device__ __noinline__ bool visit_subtree(const MapNode* __restrict__ no
     *probp = prob;
     *rowp = row;
     return ok;
-}
-
-// build_single_residual on one root record (in shared or global memory): the plane branch, or the descent.
-__device__ __forceinline__ bool eval_record(const MapNode* __restrict__ nodes, const void* rec, const PointCtx& pc,
-                                            const ScanConst& sc, const Globals& g, double& prob, Row& row) {
-    const uint32_t flags = rec_flags(rec);
-    if (flags & LK_NODE_IS_PLANE) return eval_plane_at(reinterpret_cast<const double*>(rec), pc, sc, g, false, prob, row);
-    const uint32_t cmask = (flags >> LK_NODE_CHILDMASK_SHIFT) & 0xffu;
-    const int cb = rec_child_base(rec);
-    if (g.max_layer >= 1 && cb >= 0 && cmask) return visit_subtree(nodes, cb, cmask, &pc, &sc, &g, &prob, &row);
-    return false;
-}
-__device__ __forceinline__ bool eval_record(const MapNode* __restrict__ nodes, const void* rec, const PointCtx& pc,
-                                            const ScanConst& sc, const Globals& g, Row& row) {
-    double prob = 0.0;
-    return eval_record(nodes, rec, pc, sc, g, prob, row);
 }
 
 // One point through rows a3-a7. Returns true when a residual row was produced.
@@ -202,7 +208,15 @@ __device__ __forceinline__ bool point_row(float4 pt, const ScanConst& sc, const 
     // home voxel first; on failure ONE (possibly diagonal) neighbour (KILO.cc:156-178)
 #pragma unroll 1
     for (int attempt = 0; attempt < 2; ++attempt) {
-        ok = eval_record(a.nodes, a.nodes + root, pc, sc, g, prob, row);
+        PlaneRec r;
+        load_plane(a.nodes + root, r);
+        if (r.flags & LK_NODE_IS_PLANE) {
+            ok = eval_plane(r, pc, sc, g, false, prob, row);
+        } else {
+            uint32_t cmask = (r.flags >> LK_NODE_CHILDMASK_SHIFT) & 0xffu;
+            if (g.max_layer >= 1 && r.child_base >= 0 && cmask)
+                ok = visit_subtree(a.nodes, r.child_base, cmask, &pc, &sc, &g, &prob, &row);
+        }
         if (ok || attempt == 1) break;
         // loc in VOXEL units against a centre in METRES: the reference's own unit mismatch
         double q = (double)(g.voxel_f / 4.0f);

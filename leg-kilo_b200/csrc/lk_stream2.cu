@@ -153,8 +153,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2) k_residual_stream2(const __grid
                 prepare_point(pt, sc, g, pc, lx, ly, lz);
                 const uint32_t flags = *reinterpret_cast<const uint32_t*>(slot + 224);
                 Row row;
-                double prob = 0.0;
-                if ((flags & LK_NODE_IS_PLANE) && eval_plane_at(reinterpret_cast<const double*>(slot), pc, sc, g, false, prob, row)) accumulate_row(row, acc);
+                if ((flags & LK_NODE_IS_PLANE) && eval_plane_staged(slot, pc, sc, g, row)) accumulate_row(row, acc);
                 else fail = true;  // not a plane here, or gated out: finished below with the full reference sequence
             }
             const uint32_t m = __ballot_sync(0xffffffffu, fail);

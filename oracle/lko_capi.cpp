@@ -7,7 +7,11 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <malloc.h>
+#include <pthread.h>
+#include <sched.h>
 #include <thread>
+#include <unistd.h>
 
 #include "../include/legkilo_b200.h"
 #include "lko_core.hpp"
@@ -464,7 +468,26 @@ double lko_batch_run(void* h, int batch, const lk_state* x_in, const double* P_i
                      int gain_mode, int nthreads, lk_state* x_out, double* P_out, uint32_t* n_eff_out) {
     Ctx* c = (Ctx*)h;
     if (nthreads < 1) nthreads = 1;
+    {
+        // The loop allocates tens of MB per scan (pointWithVar is 384 B, KILO.cc:120). With glibc's default thresholds
+        // every such vector is an mmap / munmap pair, and 100+ threads then fight over the process's mm lock (a 5x
+        // box-to-box swing of the all-core figure in round 1). Keep large blocks in the per-thread arenas instead.
+        static bool tuned = false;
+        if (!tuned) {
+            mallopt(M_MMAP_THRESHOLD, 1 << 30);
+            mallopt(M_TRIM_THRESHOLD, 1 << 30);
+            mallopt(M_ARENA_MAX, 256);
+            tuned = true;
+        }
+    }
+    const long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
     auto worker = [&](int tid) {
+        if (nthreads > 1 && ncpu > 0) {  // one scan loop per hardware thread, pinned
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            CPU_SET((int)(tid % ncpu), &set);
+            pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+        }
         KILO k(c->ec, c->map, c->extR, c->extT);
         k.gain_mode_ = gain_mode ? GAIN_INFORMATION : GAIN_LITERAL;
         k.iters_ = iters;

@@ -196,8 +196,11 @@ def test_every_point_gated_out():
     :212-224)."""
     cfg, blob, _ = scenes.planar_scene(n=16)
     R, t = abi.extrinsics(cfg)
-    pts = synth.planar_scan(n=1024, radius=6.0, ext_R=R, ext_t=t, stream=3, rotvec=(0, 0, 0), trans=(0, 0, 0.22))
+    pts = synth.planar_scan(n=1024, radius=4.0, ext_R=R, ext_t=t, stream=3, rotvec=(0, 0, 0), trans=(0, 0, 0.23))
     x0 = abi.default_states(1); P0 = abi.init_cov(1)
+    first, _, _, _ = _oracle(cfg, blob, pts, x0, P0, 1)
+    pts = pts[first["ok"] == 0]  # the odd grazing ray whose 3-sigma band is wider than the offset
+    assert len(pts) > 1000
     ro, _ = _check_all_paths(cfg, blob, pts, iters=3, expect_rows=False)
     assert ro["n_eff"] == 0
     eng = Engine(cfg); eng.map_upload(blob)

@@ -21,7 +21,7 @@ for scan in (3, 4, 5):
     eng.run_range(scan, 1, iters=3); eng.sync()
     tr = np.zeros((1 << 16) * 8, np.uint64); lib().lk_debug_read(eng.h, 2, _p(tr), tr.nbytes)
     nb = int((wl["offs"][scan + 1] - wl["offs"][scan] + 255) // 256)
-    nbg = (nb + 7) // 8 * 8 if CL else nb   # grid (clusters of 8)
+    nbg = nb
     b = tr[:nb * 32].reshape(nb, 32).astype(np.int64); t0 = b[:, 0].min()
     print("scan %d (%d blocks): start spread %.2f, load filter + init %.2f" % (scan, nb, us(b[:, 0].max() - t0), us(np.median(b[:, 1] - b[:, 0]))))
     prev = b[:, 1]
