@@ -218,6 +218,7 @@ ResidualArgs residual_args(lk_context* c, const ChunkDesc* chunks) {
     a.slots = c->map.slots;
     a.hash_mask = (uint32_t)(c->map.hash_cap - 1);
     a.nodes = c->map.nodes;
+    a.hot = c->map.hot;
     a.chunks = chunks;
     a.sc = c->sc.as<ScanConst>();
     a.step = c->step.as<ScanStep>();

@@ -30,6 +30,40 @@ typedef lk_map_node MapNode;   // 256 B, first 232 B are what the residual kerne
 typedef lk_map_aux MapAux;     // 64 B
 typedef lk_map_point MapPoint; // 72 B
 
+// Hot image of a plane, 160-byte stride (five 32-byte sectors, 144 bytes used): what the throughput kernel gathers per
+// point instead of the 256-byte node record. With J = [a, -n], a = pw - c:
+//     J Sigma_plane J^T = a^T Scc a - 2 a^T (Scn n) + n^T Snn n = a^T Scc a - 2 a^T v + s,
+// so the 21 covariance terms collapse to Scc (6), v = Scn n (3) and s = n^T Snn n (1), which do not depend on the point.
+// radius < 0 <=> the node holds no plane (the kernel then takes the full reference sequence on the node records).
+struct __align__(32) HotRec {
+    double c[3], n[3];
+    double scc[6];  // xx xy xz yy yz zz of the centre block of plane_var
+    double v[3];
+    double s;
+    float d, radius;
+    uint32_t pad[6];
+};
+static_assert(sizeof(HotRec) == 160, "hot record stride");
+
+__host__ __device__ inline void hot_fill(const lk_map_node& nd, HotRec& h) {  // nd holds a plane
+    const double* pv = nd.plane_var;  // upper triangle, row-major: row r starts at r*6 - r(r-1)/2
+    const double n0 = nd.normal[0], n1 = nd.normal[1], n2 = nd.normal[2];
+    for (int i = 0; i < 3; ++i) { h.c[i] = nd.center[i]; h.n[i] = nd.normal[i]; }
+    h.scc[0] = pv[0]; h.scc[1] = pv[1]; h.scc[2] = pv[2]; h.scc[3] = pv[6]; h.scc[4] = pv[7]; h.scc[5] = pv[11];
+    // Scn rows: (0,3..5) = pv[3..5], (1,3..5) = pv[8..10], (2,3..5) = pv[12..14]
+    h.v[0] = pv[3] * n0 + pv[4] * n1 + pv[5] * n2;
+    h.v[1] = pv[8] * n0 + pv[9] * n1 + pv[10] * n2;
+    h.v[2] = pv[12] * n0 + pv[13] * n1 + pv[14] * n2;
+    // Snn: (3,3) pv[15] (3,4) pv[16] (3,5) pv[17] (4,4) pv[18] (4,5) pv[19] (5,5) pv[20]
+    h.s = pv[15] * n0 * n0 + pv[18] * n1 * n1 + pv[20] * n2 * n2 + 2.0 * (pv[16] * n0 * n1 + pv[17] * n0 * n2 + pv[19] * n1 * n2);
+    h.d = nd.d;
+    h.radius = nd.radius;
+}
+__host__ __device__ inline void hot_from_node(const lk_map_node& nd, HotRec& h) {
+    if (nd.flags & LK_NODE_IS_PLANE) hot_fill(nd, h);
+    else h.radius = -1.0f;
+}
+
 struct MapView {  // what the residual path reads of the map
     const HashSlot* slots;
     uint32_t hash_mask;

@@ -22,6 +22,7 @@ struct ResidualArgs {
     const HashSlot* slots;
     uint32_t hash_mask;
     const MapNode* nodes;
+    const HotRec* hot;        // hot images of the nodes (throughput kernel)
     const ChunkDesc* chunks;  // chunk table of the whole staged batch
     uint32_t chunk_first;     // first chunk of this launch (grid.x = number of chunks)
     ScanConst* sc;            // [batch]

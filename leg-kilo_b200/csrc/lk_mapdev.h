@@ -28,6 +28,7 @@ class MapDevHost {
     HashSlot* slots = nullptr;
     MapNode* nodes = nullptr;
     MapAux* aux = nullptr;
+    HotRec* hot = nullptr;  // hot image of every node's plane (what the throughput kernel gathers)
     DevPoint* points = nullptr;
     uint32_t* counters = nullptr;  // [0] n_nodes [1] n_roots [2] overflow [4..5] n_points (u64)
     uint64_t hash_cap = 0, node_cap = 0, point_cap = 0;

@@ -39,6 +39,12 @@ __global__ void k_hash_dump(const HashSlot* slots, uint64_t capacity, lk_map_roo
     }
 }
 
+// hot images of nodes [0, n) from their node records (after a blob upload)
+__global__ void k_hot_from_nodes(const MapNode* nodes, HotRec* hot, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) hot_from_node(nodes[i], hot[i]);
+}
+
 __global__ void k_count_planes(const MapNode* nodes, const MapAux* aux, uint32_t n, unsigned long long* out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -65,10 +71,10 @@ uint64_t next_pow2(uint64_t v) {
 }  // namespace
 
 void MapDevHost::release() {
-    void* ptrs[] = {slots, nodes, aux, points, counters};
+    void* ptrs[] = {slots, nodes, aux, hot, points, counters};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    slots = nullptr; nodes = nullptr; aux = nullptr; points = nullptr; counters = nullptr;
+    slots = nullptr; nodes = nullptr; aux = nullptr; hot = nullptr; points = nullptr; counters = nullptr;
     hash_cap = node_cap = point_cap = 0;
     n_roots = n_nodes = 0;
     n_points = 0;
@@ -80,6 +86,7 @@ MapDev MapDevHost::dev() const {
     d.hash_mask = (uint32_t)(hash_cap - 1);
     d.nodes = nodes;
     d.aux = aux;
+    d.hot = hot;
     d.points = points;
     d.node_cap = (uint32_t)node_cap;
     d.point_cap = point_cap;
@@ -107,9 +114,11 @@ int MapDevHost::allocate(uint64_t roots, uint64_t nnodes, uint64_t npoints, cuda
     if (want_nodes > node_cap) {
         if (nodes) cudaFree(nodes);
         if (aux) cudaFree(aux);
-        nodes = nullptr; aux = nullptr; node_cap = 0;
+        if (hot) cudaFree(hot);
+        nodes = nullptr; aux = nullptr; hot = nullptr; node_cap = 0;
         MI_CUDA(cudaMalloc((void**)&nodes, want_nodes * sizeof(MapNode)));
         MI_CUDA(cudaMalloc((void**)&aux, want_nodes * sizeof(MapAux)));
+        MI_CUDA(cudaMalloc((void**)&hot, want_nodes * sizeof(HotRec)));
         node_cap = want_nodes;
     }
     if (want_points > point_cap) {
@@ -135,13 +144,16 @@ int MapDevHost::ensure_headroom(uint64_t extra_roots, uint64_t extra_nodes, uint
         if (want >= (1ull << 31)) { err = "node pool too large"; return LK_ERR_CAPACITY; }
         MapNode* nn = nullptr;
         MapAux* na = nullptr;
+        HotRec* nh = nullptr;
         MI_CUDA(cudaMalloc((void**)&nn, want * sizeof(MapNode)));
         MI_CUDA(cudaMalloc((void**)&na, want * sizeof(MapAux)));
+        MI_CUDA(cudaMalloc((void**)&nh, want * sizeof(HotRec)));
         MI_CUDA(cudaMemcpyAsync(nn, nodes, (size_t)n_nodes * sizeof(MapNode), cudaMemcpyDeviceToDevice, s));
         MI_CUDA(cudaMemcpyAsync(na, aux, (size_t)n_nodes * sizeof(MapAux), cudaMemcpyDeviceToDevice, s));
+        MI_CUDA(cudaMemcpyAsync(nh, hot, (size_t)n_nodes * sizeof(HotRec), cudaMemcpyDeviceToDevice, s));
         MI_CUDA(cudaStreamSynchronize(s));
-        cudaFree(nodes); cudaFree(aux);
-        nodes = nn; aux = na; node_cap = want;
+        cudaFree(nodes); cudaFree(aux); cudaFree(hot);
+        nodes = nn; aux = na; hot = nh; node_cap = want;
     }
     if (n_points + extra_points > point_cap) {
         uint64_t want = std::max<uint64_t>(n_points + extra_points, point_cap + point_cap / 2);
@@ -259,6 +271,7 @@ int map_upload_blob(MapDevHost& mh, const Globals& g, const void* blob, size_t b
         e = cudaMemcpyAsync(d_roots, roots, (size_t)hd.n_roots * sizeof(lk_map_root), cudaMemcpyHostToDevice, s);
         k_hash_insert_roots<<<(hd.n_roots + 255) / 256, 256, 0, s>>>(mh.slots, (uint32_t)(mh.hash_cap - 1), d_roots, hd.n_roots, mh.counters + 2);
     }
+    if (e == cudaSuccess && hd.n_nodes) k_hot_from_nodes<<<(hd.n_nodes + 255) / 256, 256, 0, s>>>(mh.nodes, mh.hot, hd.n_nodes);
     uint32_t ovf = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&ovf, mh.counters + 2, 4, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);

@@ -36,6 +36,14 @@ __device__ __forceinline__ int hash_find_dev(const HashSlot* slots, uint32_t mas
 
 __device__ __forceinline__ int even_up(int v) { return (v + 1) & ~1; }
 
+// keep the node's hot image (lk_device.cuh: HotRec) in step with a plane fit; lane 0 wrote the node record
+__device__ __forceinline__ void hot_after_fit(MapDev& md, uint32_t nd, bool is_plane, int lane) {
+    if (lane == 0) {
+        if (is_plane) hot_fill(md.nodes[nd], md.hot[nd]);
+        else md.hot[nd].radius = -1.0f;
+    }
+}
+
 __device__ __forceinline__ void node_reset(MapDev& md, uint32_t nd, int layer, int parent) {
     MapNode* n = md.nodes + nd;
     double* z = reinterpret_cast<double*>(n);
@@ -43,6 +51,7 @@ __device__ __forceinline__ void node_reset(MapDev& md, uint32_t nd, int layer, i
     for (int i = 0; i < 32; ++i) z[i] = 0.0;
     n->flags = LK_NODE_UPDATE_ENABLE | ((uint32_t)layer << LK_NODE_LAYER_SHIFT);  // ctor: update_enable_ = true
     n->child_base = -1;
+    md.hot[nd].radius = -1.0f;  // no plane yet
     MapAux* a = md.aux + nd;
     a->pts_base = 0; a->pts_count = 0; a->pts_cap = 0; a->new_points = 0; a->parent = parent;
     a->key[0] = a->key[1] = a->key[2] = 0; a->pad = 0;
@@ -224,6 +233,7 @@ __device__ inline void warp_init_octo_tree(MapDev& md, const Globals& g, WarpTil
         __syncwarp();
         if (cnt > thr) {
             const bool is_plane = warp_fit_plane(wt, src, cnt, md.nodes + nd, g.planer_threshold, lane);
+            hot_after_fit(md, nd, is_plane, lane);
             if (is_plane) {
                 if (cnt > g.max_points_num) {  // freeze and free (:126-130)
                     if (lane == 0) {
@@ -316,6 +326,7 @@ __device__ inline void warp_update_octo_tree(MapDev& md, const Globals& g, WarpT
                 if (newp > 5) {  // update_size_threshold_ = 5 (voxel_map.h:157)
                     const bool pl = warp_fit_plane(wt, md.points + md.aux[nd].pts_base, cnt, md.nodes + nd,
                                                    g.planer_threshold, lane);
+                    hot_after_fit(md, nd, pl, lane);
                     if (lane == 0) {
                         uint32_t f = md.nodes[nd].flags;
                         md.nodes[nd].flags = pl ? (f | LK_NODE_IS_PLANE) : (f & ~LK_NODE_IS_PLANE);

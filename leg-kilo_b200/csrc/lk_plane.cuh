@@ -24,6 +24,7 @@ struct MapDev {
     uint32_t hash_mask;
     MapNode* nodes;
     MapAux* aux;
+    HotRec* hot;  // one per node (lk_device.cuh)
     DevPoint* points;
     uint32_t node_cap;
     unsigned long long point_cap;

@@ -18,10 +18,17 @@ namespace lk {
 namespace {
 
 constexpr int S2_MAXPTS = 2048;  // largest chunk lk_api.cu hands out
-constexpr int S2_STAGE_BYTES = 32 * TILE_STRIDE;
-// slot of a lane: bytes 0..239 of the plane record (fields end at 232) | root index at 240 | point at 256
-constexpr int S2_SLOT_ROOT = 240, S2_SLOT_PT = 256;
-static_assert(TILE_STRIDE == 272, "slot layout");
+// slot of a lane: the 144 used bytes of the plane's hot image (lk_device.cuh: HotRec) | root index at 144 | point at 160.
+// 176-byte stride = 11 x 16 B: the 128-bit reads of 8 consecutive lanes fall into 8 disjoint groups of 4 banks.
+constexpr int S2_STRIDE = 176, S2_SLOT_ROOT = 144, S2_SLOT_PT = 160, S2_REC_PIECES = 9;
+constexpr int S2_STAGE_BYTES = 32 * S2_STRIDE;
+
+struct Probe {  // what stage B leaves for stage C
+    float4 pt;
+    SlotPair pair;
+    int kx, ky, kz;
+    uint32_t ih;
+};
 
 template <int S2_WARPS>
 struct S2Smem {
@@ -38,26 +45,62 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// One warp instruction of the cooperative gather: records of lanes 2*JJ and 2*JJ+1 (16 sub-lanes x 16 bytes
-// each). r >= thr with thr = 0 for the 15 copying sub-lanes and INT_MAX for the 16th: one predicate, one wide
-// multiply-add for the source address, one predicated copy.
+// One warp instruction of the cooperative gather: the hot images of lanes 3*JJ .. 3*JJ+2, nine 16-byte pieces each
+// (lanes 0-8, 9-17, 18-26; lanes 27-31 idle). r >= thr with thr = 0 for a copying lane and INT_MAX for an idle one:
+// one predicate, one wide multiply-add for the source address, one predicated copy.
 template <int JJ>
-__device__ __forceinline__ void gather_pair(int r, const unsigned char* nodes_sub, uint32_t dst0, int thr) {
+__device__ __forceinline__ void gather_triple(int r, const unsigned char* hot_sub, uint32_t dst0, int thr) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .b64 a;\n\t"
         "setp.ge.s32 p, %0, %3;\n\t"
-        "mad.wide.u32 a, %0, 256, %1;\n\t"
+        "mad.wide.u32 a, %0, 160, %1;\n\t"
         "@p cp.async.cg.shared.global [%2+%4], [a], 16;\n\t}" ::"r"(r),
-        "l"(nodes_sub), "r"(dst0), "r"(thr), "n"(JJ * 2 * TILE_STRIDE)
+        "l"(hot_sub), "r"(dst0), "r"(thr), "n"(JJ * 3 * S2_STRIDE)
         : "memory");
 }
 
-struct Probe {  // what stage B leaves for stage C
-    float4 pt;
-    SlotPair pair;
-    int kx, ky, kz;
-    uint32_t ih;
-};
+// The plane branch of build_single_residual (voxel_map.cc:370-411) + the row of KILO.cc:192-209 on a staged hot image:
+// sigma_plane = a^T Scc a - 2 a^T v + s (lk_device.cuh: HotRec). Everything else as eval_plane.
+__device__ __forceinline__ bool eval_plane_hot(const unsigned char* slot, const PointCtx& pc, const ScanConst& sc, const Globals& g,
+                                               Row& row) {
+    const double* q = reinterpret_cast<const double*>(slot);
+    const float2 dr = *reinterpret_cast<const float2*>(q + 16);
+    if (dr.y < 0.0f) return false;  // no plane in this node
+    const double2 v0 = *reinterpret_cast<const double2*>(q), v1 = *reinterpret_cast<const double2*>(q + 2),
+                  v2 = *reinterpret_cast<const double2*>(q + 4);
+    const double c0 = v0.x, c1 = v0.y, c2 = v1.x, n0 = v1.y, n1 = v2.x, n2 = v2.y;
+    const double s = n0 * pc.pwx + n1 * pc.pwy + n2 * pc.pwz + (double)dr.x;
+    const float dis = (float)fabs(s);
+    const double ax = pc.pwx - c0, ay = pc.pwy - c1, az = pc.pwz - c2;
+    const float dc = (float)(ax * ax + ay * ay + az * az);
+    const float rd = sqrtf(__fsub_rn(dc, __fmul_rn(dis, dis)));
+    if (!((double)rd <= 3.0 * (double)dr.y)) return false;
+    const double sigma_pl = quad_sym3(q + 6, ax, ay, az) - 2.0 * (ax * q[12] + ay * q[13] + az * q[14]) + q[15];
+    const double qx = sc.R[0] * n0 + sc.R[3] * n1 + sc.R[6] * n2;
+    const double qy = sc.R[1] * n0 + sc.R[4] * n1 + sc.R[7] * n2;
+    const double qz = sc.R[2] * n0 + sc.R[5] * n1 + sc.R[8] * n2;
+    const double hx = pc.piy * qz - pc.piz * qy, hy = pc.piz * qx - pc.pix * qz, hz = pc.pix * qy - pc.piy * qx;
+    const double wx = g.Re[0] * qx + g.Re[3] * qy + g.Re[6] * qz;
+    const double wy = g.Re[1] * qx + g.Re[4] * qy + g.Re[7] * qz;
+    const double wz = g.Re[2] * qx + g.Re[5] * qy + g.Re[8] * qz;
+    const double uw = pc.pbx * wx + pc.pby * wy + pc.pbz * wz;
+    const double ww = wx * wx + wy * wy + wz * wz;
+    const double uw2 = uw * uw / pc.r2;
+    const double body = (double)g.rv * uw2 + pc.range2 * g.dv * (ww - uw2);
+    const double state = quad_sym3(sc.Pth, hx, hy, hz) + quad_sym3(sc.Ppp, n0, n1, n2);
+    const double sigma_l = sigma_pl + body + state;
+    const double lhs = (double)dis * (double)dis;
+    const double rhs = g.sigma_num * g.sigma_num * sigma_l;
+    bool pass;
+    if (lhs < rhs * (1.0 - 1e-12)) pass = true;
+    else if (lhs > rhs * (1.0 + 1e-12)) pass = false;
+    else pass = (double)dis < g.sigma_num * sqrt(sigma_l);
+    if (!pass) return false;
+    row.h[0] = hx; row.h[1] = hy; row.h[2] = hz; row.h[3] = n0; row.h[4] = n1; row.h[5] = n2;
+    row.z = -(double)(float)s;
+    row.R = g.ratio * (sigma_pl + body);
+    return true;
+}
 
 template <int S2_THREADS>
 __global__ void __launch_bounds__(S2_THREADS, 2) k_residual_stream2(const __grid_constant__ ResidualArgs a) {
@@ -75,12 +118,13 @@ __global__ void __launch_bounds__(S2_THREADS, 2) k_residual_stream2(const __grid
     const float4* __restrict__ pts = a.pts + cd.start;
     const uint32_t count = cd.count;
 
-    const int half = lane >> 4, sub = lane & 15;
+    const int third = lane / S2_REC_PIECES, sub = lane % S2_REC_PIECES;  // third == 3: lanes 27-31 never copy
     const uint32_t st_base = smem_u32(&sm->st[warp][0][0]);
-    const uint32_t slot_off = (uint32_t)lane * TILE_STRIDE;
-    const uint32_t copy_off = (uint32_t)half * TILE_STRIDE + (uint32_t)sub * 16u;
-    const unsigned char* nodes_sub = reinterpret_cast<const unsigned char*>(mv.nodes) + sub * 16;
-    const int thr = sub < 15 ? 0 : 0x7fffffff;
+    const uint32_t slot_off = (uint32_t)lane * S2_STRIDE;
+    const uint32_t copy_off = (uint32_t)(third % 3) * S2_STRIDE + (uint32_t)sub * 16u;
+    const unsigned char* hot_sub = reinterpret_cast<const unsigned char*>(a.hot) + sub * 16;
+    const int thr = third < 3 ? 0 : 0x7fffffff;
+    const int thr_last = third < 2 ? 0 : 0x7fffffff;  // the 11th instruction carries lanes 30, 31 only
 
     double acc[32];
 #pragma unroll
@@ -113,9 +157,8 @@ __global__ void __launch_bounds__(S2_THREADS, 2) k_residual_stream2(const __grid
                          "f"(pr.pt.z), "f"(pr.pt.w) : "memory");
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(stage + slot_off + S2_SLOT_ROOT), "r"(root) : "memory");
             const uint32_t dst0 = stage + copy_off;
-#define LK_G(JJ) gather_pair<JJ>(__shfl_sync(0xffffffffu, root, 2 * JJ + half), nodes_sub, dst0, thr);
-            LK_G(0) LK_G(1) LK_G(2) LK_G(3) LK_G(4) LK_G(5) LK_G(6) LK_G(7)
-            LK_G(8) LK_G(9) LK_G(10) LK_G(11) LK_G(12) LK_G(13) LK_G(14) LK_G(15)
+#define LK_G(JJ) gather_triple<JJ>(__shfl_sync(0xffffffffu, root, (3 * JJ + third) & 31), hot_sub, dst0, (JJ) == 10 ? thr_last : thr);
+            LK_G(0) LK_G(1) LK_G(2) LK_G(3) LK_G(4) LK_G(5) LK_G(6) LK_G(7) LK_G(8) LK_G(9) LK_G(10)
 #undef LK_G
         }
         cp_async_commit();
@@ -143,7 +186,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2) k_residual_stream2(const __grid
         cp_async_wait_group<1>();         // gather(i) has landed (this lane's copies) ...
         __syncwarp();                     // ... and everybody else's
         {
-            const unsigned char* slot = &sm->st[warp][i & 1u][0] + (size_t)lane * TILE_STRIDE;
+            const unsigned char* slot = &sm->st[warp][i & 1u][0] + (size_t)lane * S2_STRIDE;
             const int root = *reinterpret_cast<const int*>(slot + S2_SLOT_ROOT);
             bool fail = false;
             if (root >= 0) {
@@ -151,9 +194,8 @@ __global__ void __launch_bounds__(S2_THREADS, 2) k_residual_stream2(const __grid
                 PointCtx pc;
                 float lx, ly, lz;
                 prepare_point(pt, sc, g, pc, lx, ly, lz);
-                const uint32_t flags = *reinterpret_cast<const uint32_t*>(slot + 224);
                 Row row;
-                if ((flags & LK_NODE_IS_PLANE) && eval_plane_staged(slot, pc, sc, g, row)) accumulate_row(row, acc);
+                if (eval_plane_hot(slot, pc, sc, g, row)) accumulate_row(row, acc);
                 else fail = true;  // not a plane here, or gated out: finished below with the full reference sequence
             }
             const uint32_t m = __ballot_sync(0xffffffffu, fail);
