@@ -690,7 +690,19 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         const uint64_t n = h->h_scan_pts[first];
         std::string err;
         int rc = h->map.ready() ? h->map.sync_counters(s, err) : LK_OK;
-        if (!rc) rc = h->map.ensure_headroom(n + 16, 4 * n + 64, 60 * n + 64, s, err);
+        // Worst case of UpdateVoxelMap per inserted point (lk_octree.cuh): a new root (1 node, one tile); per octree level one
+        // cut (8 nodes) whose children each get a tile — at most threshold + 1 of them hold a point when the cut fires; a
+        // tile is max_points_num + 2 slots (even). Reserving the bound makes a mid-insert overflow impossible: no point is
+        // ever dropped (the pools only grow when a scan could actually exceed them: 180 GB of HBM is the budget).
+        if (!rc) {
+            const Globals& g = h->g;
+            int thr = 0;
+            for (int l = 0; l < 5; ++l) thr = std::max(thr, g.layer_init_num[l]);
+            const uint64_t tile = (uint64_t)((g.max_points_num + 2 + 1) & ~1);
+            const uint64_t per_pt_nodes = 1 + 8ull * (uint64_t)std::max(g.max_layer, 0);
+            const uint64_t per_pt_slots = tile * (1 + (uint64_t)std::max(g.max_layer, 0) * (uint64_t)std::min(8, thr + 1)) + 2;
+            rc = h->map.ensure_headroom(n + 16, per_pt_nodes * n + 64, per_pt_slots * n + 64, s, err);
+        }
         if (!rc) rc = h->map.push_counters(s, err);
         if (rc) return fail(h, rc, err);
         for (uint32_t k = 0; k < h->n_steps; ++k) {

@@ -39,6 +39,14 @@ __global__ void k_hash_dump(const HashSlot* slots, uint64_t capacity, lk_map_roo
     }
 }
 
+// every root key must resolve to its own node: a second root with the same key is unreachable (and means a corrupt blob)
+__global__ void k_check_roots(const HashSlot* slots, uint32_t mask, const lk_map_root* roots, uint32_t n, uint32_t* ovf) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    lk_map_root r = roots[i];
+    if (hash_find_dev(slots, mask, r.key[0], r.key[1], r.key[2]) != r.node) atomicOr(ovf, 8u);
+}
+
 // hot images of nodes [0, n) from their node records (after a blob upload)
 __global__ void k_hot_from_nodes(const MapNode* nodes, HotRec* hot, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -236,6 +244,11 @@ int map_upload_blob(MapDevHost& mh, const Globals& g, const void* blob, size_t b
         lk_map_aux& a = aux2[i];
         if ((uint64_t)a.pts_base + (uint64_t)std::max(a.pts_count, 0) > hd.n_points) { err = "node point range out of bounds"; return LK_ERR_BAD_BLOB; }
         int layer = (n.flags >> LK_NODE_LAYER_SHIFT) & 0xff;
+        const uint32_t cmask = (n.flags >> LK_NODE_CHILDMASK_SHIFT) & 0xffu;
+        // the residual kernels follow child_base / the child mask without further checks
+        if (layer > g.max_layer || layer > 4) { err = "node layer exceeds max_layer"; return LK_ERR_BAD_BLOB; }
+        if (n.child_base < -1 || (n.child_base >= 0 && (uint64_t)n.child_base + 8 > hd.n_nodes)) { err = "node child_base out of range"; return LK_ERR_BAD_BLOB; }
+        if (cmask && n.child_base < 0) { err = "node has a child mask but no children"; return LK_ERR_BAD_BLOB; }
         bool init = n.flags & LK_NODE_INIT_OCTO, plane = n.flags & LK_NODE_IS_PLANE, upd = n.flags & LK_NODE_UPDATE_ENABLE;
         bool interior = init && !plane && layer < g.max_layer;
         bool can_grow = !init || (upd && !interior);
@@ -270,6 +283,7 @@ int map_upload_blob(MapDevHost& mh, const Globals& g, const void* blob, size_t b
     if (e == cudaSuccess && hd.n_roots) {
         e = cudaMemcpyAsync(d_roots, roots, (size_t)hd.n_roots * sizeof(lk_map_root), cudaMemcpyHostToDevice, s);
         k_hash_insert_roots<<<(hd.n_roots + 255) / 256, 256, 0, s>>>(mh.slots, (uint32_t)(mh.hash_cap - 1), d_roots, hd.n_roots, mh.counters + 2);
+        k_check_roots<<<(hd.n_roots + 255) / 256, 256, 0, s>>>(mh.slots, (uint32_t)(mh.hash_cap - 1), d_roots, hd.n_roots, mh.counters + 2);
     }
     if (e == cudaSuccess && hd.n_nodes) k_hot_from_nodes<<<(hd.n_nodes + 255) / 256, 256, 0, s>>>(mh.nodes, mh.hot, hd.n_nodes);
     uint32_t ovf = 0;
@@ -277,6 +291,7 @@ int map_upload_blob(MapDevHost& mh, const Globals& g, const void* blob, size_t b
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     cudaFree(d_roots);
     if (e != cudaSuccess) { cudaGetLastError(); err = cudaGetErrorString(e); return LK_ERR_CUDA; }
+    if (ovf & 8u) { err = "duplicate root keys in the blob"; return LK_ERR_BAD_BLOB; }
     if (ovf) { err = "root table overflow"; return LK_ERR_CAPACITY; }
     mh.n_roots = hd.n_roots;
     mh.n_nodes = hd.n_nodes;

@@ -86,3 +86,37 @@ def test_argument_errors_are_status_codes_and_the_handle_survives():
     ro, xo, Po = _oracle(cfg, blob, s, x1, P1, 2)
     assert int(out["n_eff"][0]) == ro["n_eff"] > 0
     assert scenes.rel_state_err(out["x"], xo, x1) < TOL
+
+
+def test_corrupt_map_blobs_are_rejected():
+    """lk_map_upload validates what the kernels later follow blindly: child indices, layers, child masks without children,
+    and two roots with one key (the second would be unreachable). A rejected upload leaves the handle usable."""
+    cfg, blob, scans = scenes.box_scene(batch=1)
+    hd, roots, nodes, aux, pts = abi.parse_map_blob(blob)
+    eng = Engine(cfg)
+
+    def bad(mut):
+        r, n, a = roots.copy(), nodes.copy(), aux.copy()
+        mut(r, n, a)
+        with pytest.raises(LkError) as e:
+            eng.map_upload(abi.make_map_blob(r, n, a, pts))
+        assert e.value.code == -5, e.value  # LK_ERR_BAD_BLOB
+
+    def child_out_of_range(r, n, a):
+        n["child_base"][3] = len(n) - 4
+    def negative_child(r, n, a):
+        n["child_base"][3] = -7
+    def mask_without_children(r, n, a):
+        n["flags"][5] = (int(n["flags"][5]) | (0x21 << 16)); n["child_base"][5] = -1
+    def layer_too_deep(r, n, a):
+        n["flags"][7] = (int(n["flags"][7]) & ~0xFF00) | (4 << 8)
+    def duplicate_root(r, n, a):
+        r["key"][1] = r["key"][0]
+    def root_node_out_of_range(r, n, a):
+        r["node"][2] = len(n)
+    for m in (child_out_of_range, negative_child, mask_without_children, layer_too_deep, duplicate_root, root_node_out_of_range):
+        bad(m)
+    eng.map_upload(blob)  # the handle survived all of that
+    x0 = abi.default_states(1); P0 = abi.init_cov(1)
+    out = eng.scan_update(x0, P0, abi.process_cov_Q(cfg), np.zeros(1, abi.CLOCK_DTYPE), scans[0], [0, len(scans[0])], [0.0])
+    assert int(out["n_eff"][0]) > 0
