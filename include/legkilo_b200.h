@@ -220,6 +220,12 @@ int lk_map_build(lk_handle h, const float* xyz_world, const float* xyz_body, siz
                  const double rot[9], const double rot_cov[9], const double pos_cov[9]);
 /* Map counters: out[0]=roots, out[1]=nodes, out[2]=retained points, out[3]=plane nodes. */
 int lk_map_stats(lk_handle h, uint64_t out[4]);
+/* VoxelMapManager::mapSliding + clearMemOutOfMap (voxel_map.cc:552-594; dead code in the reference, needed for unbounded
+ * runs): when `position` is at least sliding_thresh away from the position of the last slide (initially the origin,
+ * voxel_map.h:201), every root voxel whose key lies outside [k - half_map_size, k + half_map_size] on some axis,
+ * k = floor(position / voxel_size) (eigen_types.hpp:89-95), is removed from the map. *slid = 1 when a slide happened,
+ * *removed = root voxels dropped. The root table is rebuilt; pool storage of the dropped octrees is not recycled. */
+int lk_map_slide(lk_handle h, const double position[3], int32_t* slid, uint64_t* removed);
 
 /* ---- the hot path ---------------------------------------------------------------------- */
 
@@ -307,6 +313,11 @@ int lk_process_scan(lk_handle h, lk_state* x_inout, double* P_inout, const doubl
                     const lk_imu_meas* imu, const lk_kinimu_meas* kin, uint32_t n_meas,
                     double gravity, double acc_norm, int iters, int update_map,
                     float* pts_world_out, uint32_t* n_effective_out, uint32_t* n_consumed);
+
+/* TrajectorySaver::write (trajectory_saver.hpp:43-50): one TUM line "timestamp tx ty tz qx qy qz qw\n", fixed notation,
+ * 9 decimals, the quaternion by Eigen's Quaterniond(Matrix3d) rule. rot = row-major body->world. Host-side helper;
+ * returns the number of characters written (excluding the NUL) or LK_ERR_CAPACITY. */
+int lk_tum_line(double timestamp, const double rot[9], const double pos[3], char* buf, size_t capacity);
 
 /* ---- what feeds the path ------------------------------------------- */
 

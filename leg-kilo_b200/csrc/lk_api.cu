@@ -86,6 +86,7 @@ struct lk_context {
 
     // map
     MapDevHost map;
+    double last_slide_position[3] = {0.0, 0.0, 0.0};  // VoxelMapManager::last_slide_position (voxel_map.h:201)
 
     // staged batch
     int batch = 0;
@@ -416,6 +417,61 @@ int lk_map_stats(lk_handle h, uint64_t out[4]) {
     out[2] = live;
     out[3] = planes;
     return LK_OK;
+}
+
+int lk_map_slide(lk_handle h, const double position[3], int32_t* slid, uint64_t* removed) {
+    if (!h || !position) return fail(h, LK_ERR_INVALID_ARG, "null argument");
+    if (slid) *slid = 0;
+    if (removed) *removed = 0;
+    cudaSetDevice(h->device);
+    h->prev_fused = false;
+    // voxel_map.cc:553: (position_last_ - last_slide_position).norm() < sliding_thresh -> nothing to do
+    double d2 = 0.0;
+    for (int k = 0; k < 3; ++k) d2 += (position[k] - h->last_slide_position[k]) * (position[k] - h->last_slide_position[k]);
+    if (std::sqrt(d2) < h->mc.sliding_thresh) return LK_OK;
+    for (int k = 0; k < 3; ++k) h->last_slide_position[k] = position[k];
+    int lo[3], hi[3];
+    for (int k = 0; k < 3; ++k) {
+        const int key = (int)std::floor(position[k] / h->mc.max_voxel_size);  // voxelKeyFloor (eigen_types.hpp:89-95)
+        lo[k] = key - h->mc.half_map_size;
+        hi[k] = key + h->mc.half_map_size;
+    }
+    std::string err;
+    int rc = map_clear_outside(h->map, lo, hi, removed, h->stream, err);
+    if (rc) return fail(h, rc, err);
+    if (slid) *slid = 1;
+    return LK_OK;
+}
+
+int lk_tum_line(double timestamp, const double rot[9], const double pos[3], char* buf, size_t capacity) {
+    if (!rot || !pos || !buf) return LK_ERR_INVALID_ARG;
+    // Eigen::Quaterniond(Matrix3d) (Eigen/src/Geometry/Quaternion.h, quaternionbase_assign_impl<Other, 3, 3>), m(i, j) = rot[3 i + j]
+    auto m = [&](int i, int j) { return rot[3 * i + j]; };
+    double q[4];  // x y z w
+    double t = m(0, 0) + m(1, 1) + m(2, 2);
+    if (t > 0.0) {
+        t = std::sqrt(t + 1.0);
+        q[3] = 0.5 * t;
+        t = 0.5 / t;
+        q[0] = (m(2, 1) - m(1, 2)) * t;
+        q[1] = (m(0, 2) - m(2, 0)) * t;
+        q[2] = (m(1, 0) - m(0, 1)) * t;
+    } else {
+        int i = 0;
+        if (m(1, 1) > m(0, 0)) i = 1;
+        if (m(2, 2) > m(i, i)) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + 1.0);
+        q[i] = 0.5 * t;
+        t = 0.5 / t;
+        q[3] = (m(k, j) - m(j, k)) * t;
+        q[j] = (m(j, i) + m(i, j)) * t;
+        q[k] = (m(k, i) + m(i, k)) * t;
+    }
+    const int n = std::snprintf(buf, capacity, "%.9f %.9f %.9f %.9f %.9f %.9f %.9f %.9f\n", timestamp, pos[0], pos[1], pos[2], q[0], q[1],
+                                q[2], q[3]);
+    if (n < 0 || (size_t)n >= capacity) return LK_ERR_CAPACITY;
+    return n;
 }
 
 int lk_map_download(lk_handle h, void* blob, size_t capacity, size_t* bytes_out) {

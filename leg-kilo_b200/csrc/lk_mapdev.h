@@ -53,5 +53,7 @@ size_t insert_point_bytes();
 int map_upload_blob(MapDevHost& mh, const Globals& g, const void* blob, size_t bytes, cudaStream_t s, std::string& err);
 int map_download_blob(MapDevHost& mh, void* blob, size_t capacity, size_t* bytes_out, cudaStream_t s, std::string& err);
 int map_count_planes(MapDevHost& mh, uint64_t* planes, uint64_t* live_points, cudaStream_t s, std::string& err);
+// drop every root whose key is outside [lo, hi] on some axis (clearMemOutOfMap, voxel_map.cc:573-594); rebuilds the table
+int map_clear_outside(MapDevHost& mh, const int lo[3], const int hi[3], uint64_t* removed, cudaStream_t s, std::string& err);
 
 }  // namespace lk

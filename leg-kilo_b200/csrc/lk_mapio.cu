@@ -363,6 +363,46 @@ int map_download_blob(MapDevHost& mh, void* blob, size_t capacity, size_t* bytes
     return LK_OK;
 }
 
+int map_clear_outside(MapDevHost& mh, const int lo[3], const int hi[3], uint64_t* removed, cudaStream_t s, std::string& err) {
+    if (removed) *removed = 0;
+    if (!mh.ready()) return LK_OK;
+    int rc = mh.sync_counters(s, err);
+    if (rc) return rc;
+    if (mh.n_roots == 0) return LK_OK;
+    lk_map_root* d_roots = nullptr;
+    uint32_t* d_cnt = nullptr;
+    MI_CUDA(cudaMalloc((void**)&d_roots, (size_t)mh.n_roots * sizeof(lk_map_root)));
+    MI_CUDA(cudaMalloc((void**)&d_cnt, 4));
+    MI_CUDA(cudaMemsetAsync(d_cnt, 0, 4, s));
+    k_hash_dump<<<(unsigned)((mh.hash_cap + 255) / 256), 256, 0, s>>>(mh.slots, mh.hash_cap, d_roots, d_cnt);
+    std::vector<lk_map_root> roots(mh.n_roots);
+    uint32_t n = 0;
+    cudaError_t e = cudaMemcpyAsync(&n, d_cnt, 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess && n) e = cudaMemcpy(roots.data(), d_roots, (size_t)std::min(n, mh.n_roots) * sizeof(lk_map_root), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { cudaFree(d_roots); cudaFree(d_cnt); cudaGetLastError(); err = cudaGetErrorString(e); return LK_ERR_CUDA; }
+    n = std::min(n, mh.n_roots);
+    uint32_t keep = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const lk_map_root& r = roots[i];
+        const bool out = r.key[0] > hi[0] || r.key[0] < lo[0] || r.key[1] > hi[1] || r.key[1] < lo[1] || r.key[2] > hi[2] || r.key[2] < lo[2];
+        if (!out) roots[keep++] = r;
+    }
+    if (removed) *removed = n - keep;
+    if (keep != n) {
+        k_hash_clear<<<(unsigned)((mh.hash_cap + 255) / 256), 256, 0, s>>>(mh.slots, mh.hash_cap);
+        if (keep) {
+            e = cudaMemcpyAsync(d_roots, roots.data(), (size_t)keep * sizeof(lk_map_root), cudaMemcpyHostToDevice, s);
+            k_hash_insert_roots<<<(keep + 255) / 256, 256, 0, s>>>(mh.slots, (uint32_t)(mh.hash_cap - 1), d_roots, keep, mh.counters + 2);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        mh.n_roots = keep;
+    }
+    cudaFree(d_roots); cudaFree(d_cnt);
+    if (e != cudaSuccess) { cudaGetLastError(); err = cudaGetErrorString(e); return LK_ERR_CUDA; }
+    return keep != n ? mh.push_counters(s, err) : LK_OK;
+}
+
 int map_count_planes(MapDevHost& mh, uint64_t* planes, uint64_t* live_points, cudaStream_t s, std::string& err) {
     *planes = 0;
     *live_points = 0;

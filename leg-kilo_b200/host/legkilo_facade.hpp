@@ -1,9 +1,10 @@
 // legkilo_facade.hpp — the reference's class names over the C ABI.
 //
-// Header-only, needs Eigen + PCL point types, i.e. it is compiled INSIDE the reference's catkin
-// workspace, not in this repository's build image (no Eigen / PCL / ROS here): everything below is
-// guarded by __has_include and is exercised only through INTEGRATION.md. The POD C ABI underneath
-// (include/legkilo_b200.h) is what tests/ cover.
+// Header-only, needs Eigen, i.e. it is compiled INSIDE the reference's catkin workspace, not in this
+// repository's build image (no Eigen / PCL / ROS here): everything below is guarded by __has_include.
+// tests/test_facade_compiles.py type-checks it and instantiates its templates against a small stand-in
+// for <Eigen/Dense> (tests/stubs/); the POD C ABI underneath (include/legkilo_b200.h) is what the parity
+// tests cover.
 //
 // Mirrors: legkilo::State / ESKF (legkilo/src/core/slam/eskf.h:15-109), VoxelMapManager
 // (legkilo/src/core/slam/voxel_map.h:180-244), and the per-scan entry KILO::process
@@ -98,6 +99,23 @@ class Core {
         if (!imu.empty()) imu.erase(imu.begin(), imu.begin() + used);  // the deque pop_front of KILO.cc:382, :388
         if (!kin.empty()) kin.erase(kin.begin(), kin.begin() + used);
         return n_eff;  // success_pts_size_out
+    }
+
+    // VoxelMapManager::mapSliding (voxel_map.cc:552-571): drop the root voxels that left the +-half_map_size window.
+    bool mapSliding(const Vec3D& position_last, uint64_t* removed = nullptr) {
+        int32_t slid = 0;
+        check(lk_map_slide(h_, position_last.data(), &slid, removed));
+        return slid != 0;
+    }
+
+    // TrajectorySaver::write (trajectory_saver.hpp:43-50): one TUM line of the current pose.
+    template <class StateT>
+    std::string tumLine(double timestamp, const StateT& state) const {
+        RowMat3 R = state.rot_;
+        char buf[256];
+        const int n = lk_tum_line(timestamp, R.data(), state.pos_.data(), buf, sizeof(buf));
+        if (n < 0) throw std::runtime_error("lk_tum_line");
+        return std::string(buf, (size_t)n);
     }
 
     lk_handle handle() const { return h_; }

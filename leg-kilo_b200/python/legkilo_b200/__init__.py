@@ -51,6 +51,8 @@ def lib():
         L.lk_map_download.argtypes = [vp, vp, C.c_size_t, vp]
         L.lk_map_build.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, vp]
         L.lk_map_stats.argtypes = [vp, vp]
+        L.lk_map_slide.argtypes = [vp, vp, vp, vp]
+        L.lk_tum_line.argtypes = [dbl, vp, vp, C.c_char_p, C.c_size_t]
         L.lk_scan_update.argtypes = [vp, i32] + [vp] * 9 + [i32, i32, vp, vp]
         L.lk_batch_stage.argtypes = [vp, i32] + [vp] * 9
         L.lk_batch_run.argtypes = [vp, i32, i32]
@@ -71,6 +73,16 @@ def lib():
         L.lk_preprocess_scan.argtypes = [vp, vp, u32, C.c_float, vp, vp, vp, vp, vp]
         _LIB = L
     return _LIB
+
+
+def tum_line(timestamp, rot, pos) -> str:
+    """TrajectorySaver::write (trajectory_saver.hpp:43-50)."""
+    rot = np.ascontiguousarray(rot, np.float64).reshape(9); pos = np.ascontiguousarray(pos, np.float64)
+    buf = C.create_string_buffer(256)
+    n = lib().lk_tum_line(float(timestamp), _p(rot), _p(pos), buf, 256)
+    if n < 0:
+        raise LkError(n, "lk_tum_line")
+    return buf.value.decode()
 
 
 def _p(a):
@@ -164,6 +176,13 @@ class Engine:
         pos_cov = 1e-6 * np.eye(3) if pos_cov is None else np.ascontiguousarray(pos_cov, np.float64)
         self._chk(lib().lk_map_build(self.h, _p(xyz_world), _p(xyz_body), len(xyz_world), _p(R), _p(rot_cov),
                                      _p(pos_cov)))
+
+    def map_slide(self, position):
+        """VoxelMapManager::mapSliding (voxel_map.cc:552-571). Returns (slid, removed root voxels)."""
+        pos = np.ascontiguousarray(position, np.float64)
+        slid = C.c_int32(0); removed = C.c_uint64(0)
+        self._chk(lib().lk_map_slide(self.h, _p(pos), C.byref(slid), C.byref(removed)))
+        return bool(slid.value), int(removed.value)
 
     def map_stats(self):
         out = np.zeros(4, np.uint64)
