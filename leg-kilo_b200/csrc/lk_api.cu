@@ -109,12 +109,13 @@ struct lk_context {
     DevBuf ll;               // flagged rows of the fused kernel's all-reduce (lk_llsync.cuh), zero-filled once
     uint32_t ll_epoch = 1;   // next unused tag (0 = the fill value, never used)
     bool prev_fused = false;  // the last operation enqueued on `stream` was a fused launch (PDL is only used then)
-    uint32_t fused_launches = 0;
+    uint32_t fused_launches = 0, fused_launches_since_check = 0;
     // direct mode of lk_scan_update (one scan, page-locked caller buffers): the kernel reads the points and
     // writes the world cloud / the filter in place, the small inputs ride in the kernel's parameter block
     int direct_io = 1, inline_in = 1, coop_launch = 0, pdl = 1, n_sms = 148, slim_p = 1;
     size_t h_off_clk = 0;  // offset of the staged clocks inside h_small_in
     int fast_insert = 1;  // update_map: two-launch insert for small buckets, re-projection folded into it
+    int fused_insert = 1;  // update_map of one scan with small buckets: UpdateVoxelMap inside the persistent kernel
     bool direct = false, direct_ran = false, inline_ok = false;
     const float4* direct_pts = nullptr;
     float4* direct_world = nullptr;
@@ -234,6 +235,29 @@ ResidualArgs residual_args(lk_context* c, const ChunkDesc* chunks) {
     return a;
 }
 
+// After a synchronisation: did a fused launch give up waiting for its peers (lk_llsync.cuh watchdog)?
+int check_stall(lk_handle h) {
+    if (!h->ll.p || !h->fused_launches_since_check) return LK_OK;
+    h->fused_launches_since_check = 0;
+    uint32_t st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    LK_CUDA(h, cudaMemcpy(st, (char*)h->ll.p + LL_ROWS_BYTES, sizeof(st), cudaMemcpyDeviceToHost));
+    uint32_t note[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (fused_read_stall(note) == 0 && note[0]) {
+        char m2[256];
+        static const char* what[] = {"", "a bulk copy never completed its mbarrier", "a root-table slot was never published",
+                                     "octree deeper than max_layer", "root table has no empty slot"};
+        std::snprintf(m2, sizeof(m2), "per-scan kernel watchdog: %s (block %u, thread %u, detail %u)", what[note[0] < 5 ? note[0] : 0],
+                      note[1], note[2], note[3]);
+        return fail(h, LK_ERR_CUDA, m2);
+    }
+    if (!st[0]) return LK_OK;
+    LK_CUDA(h, cudaMemset((char*)h->ll.p + LL_ROWS_BYTES, 0, 64));
+    char msg[320];
+    std::snprintf(msg, sizeof(msg), "per-scan kernel: block %u gave up waiting for rows [%u, %u) of exchange tag %u (lane %u): the grid was "
+                  "not fully resident (device shared with another process?)", st[1], st[3], st[3] + st[4], st[2], st[5]);
+    return fail(h, LK_ERR_CUDA, msg);
+}
+
 }  // namespace
 
 extern "C" {
@@ -343,6 +367,7 @@ int lk_set_param(lk_handle h, const char* name, double value) {
     if (!std::strcmp(name, "fused")) { h->use_fused = (int)value; return LK_OK; }
     if (!std::strcmp(name, "lane_cache")) { h->lane_cache = (int)value; return LK_OK; }
     if (!std::strcmp(name, "fast_insert")) { h->fast_insert = (int)value; return LK_OK; }
+    if (!std::strcmp(name, "fused_insert")) { h->fused_insert = (int)value; return LK_OK; }
     if (!std::strcmp(name, "coop_launch")) { h->coop_launch = (int)value; return LK_OK; }
     if (!std::strcmp(name, "pdl")) { h->pdl = (int)value; return LK_OK; }
     if (!std::strcmp(name, "slim_p")) { h->slim_p = (int)value; return LK_OK; }
@@ -382,7 +407,7 @@ int lk_sync(lk_handle h) {
     cudaSetDevice(h->device);
     h->prev_fused = false;
     LK_CUDA(h, cudaStreamSynchronize(h->stream));
-    return LK_OK;
+    return check_stall(h);
 }
 
 // ---- map ------------------------------------------------------------------------------------
@@ -702,6 +727,10 @@ int lk_timer_stop(lk_handle h, float* total_ms, float* residual_kernel_ms, uint3
     LK_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     LK_CUDA(h, cudaStreamSynchronize(h->stream));
     LK_CUDA(h, cudaGetLastError());
+    {
+        const int rc = check_stall(h);
+        if (rc) return rc;
+    }
     LK_CUDA(h, cudaEventElapsedTime(&h->last_total_ms, h->ev0, h->ev1));
     float rms = 0;
     for (size_t i = 0; i + 1 < h->nev; i += 2) {
@@ -785,9 +814,14 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
             const StepInit& in = h->h_inits[(size_t)k * batch + first];
             max_chunks = std::max(max_chunks, in.chunk_end - in.chunk_begin);
         }
-    if (count == 1 && h->use_fused && h->max_chunk_pts <= 256 && !update_map && max_chunks <= (uint32_t)fused_max_blocks(h->device)) {
-        // one scan: the whole bucket loop in ONE persistent kernel, one chunk per block (lk_fused.cu)
-        const uint32_t grid = max_chunks;
+    // update_map inside the persistent kernel: buckets of up to 4 096 points (the root-per-point scan of its insert phase)
+    const bool fused_ins = update_map && h->fast_insert && h->fused_insert && max_bucket <= 4096u;
+    if (count == 1 && h->use_fused && h->max_chunk_pts <= 256 && (!update_map || fused_ins) &&
+        max_chunks <= (uint32_t)fused_max_blocks(h->device)) {
+        // one scan: the whole bucket loop in ONE persistent kernel, one chunk per block (lk_fused.cu). With the map insert
+        // inside, every SM gets a block: the buckets' points sit in the first few, but the insert phase hands one touched
+        // root voxel to every warp of the grid.
+        const uint32_t grid = fused_ins ? (uint32_t)fused_max_blocks(h->device) : max_chunks;
         FusedArgs fa;
         std::memset(&fa, 0, sizeof(fa));
         fa.pts = h->direct ? h->direct_pts : h->pts.as<float4>();
@@ -820,7 +854,7 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         fa.clk = h->clk.as<lk_stream_clock>();
         fa.n_eff = h->n_eff.as<uint32_t>();
         // tags of the flagged rows: one per (step, iteration); restart (with a cleared buffer) long before the 32-bit wrap
-        const uint32_t need = h->n_steps * (uint32_t)iters + 1u;
+        const uint32_t need = h->n_steps * ((uint32_t)iters + 2u) + 1u;  // + two barriers per bucket with the insert inside
         if (h->ll_epoch > 0xE0000000u || need > 0x10000000u) {
             if (need > 0x10000000u) return fail(h, LK_ERR_INVALID_ARG, "steps x iters too large for one launch");
             LK_CUDA(h, cudaMemsetAsync(h->ll.p, 0, LL_BYTES, s));
@@ -829,6 +863,7 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         }
         fa.ll.chunk_rows = h->ll.as<ulonglong2>();
         fa.ll.group_rows = h->ll.as<ulonglong2>() + (size_t)2 * LL_MAX_CHUNKS * LL_ROW;
+        fa.ll.stall = reinterpret_cast<uint32_t*>((char*)h->ll.p + LL_ROWS_BYTES);
         fa.epoch = h->ll_epoch;
         h->ll_epoch += need;
         fa.iters = iters;
@@ -853,6 +888,16 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         fa.ecfg = h->ec;
         fa.trace = h->trace_on ? h->trace.as<unsigned long long>() : nullptr;
         fa.g = h->g;
+        if (update_map) {
+            fa.insert = 1;
+            fa.md = h->map.dev();
+            fa.ipts = reinterpret_cast<DevPoint*>(h->ins_pts.p);
+            fa.iroot = h->ins_root.as<int>();
+            fa.pend = h->ins_pend.as<int>();
+            fa.touched = h->ins_touched.as<uint32_t>();
+            fa.ins_counters = h->ins_counters.as<uint32_t>() + 2;  // zeroed above, as for the two-launch insert
+            h->prev_fused = false;  // the counters were cleared by a memset on the stream
+        }
         if (h->kernel_timing) { cudaEventRecord(kev_get(h, h->nev++), s); h->prev_fused = false; }
         const int mode = h->coop_launch ? FUSED_LAUNCH_COOPERATIVE : ((h->pdl && h->prev_fused) ? FUSED_LAUNCH_PDL : FUSED_LAUNCH_PLAIN);
         {
@@ -870,10 +915,22 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
             LK_CUDA(h, launch_scan_fused(fa, inl, grid, s, mode));
         }
         h->prev_fused = true;
+        ++h->fused_launches_since_check;
         if (h->kernel_timing) { cudaEventRecord(kev_get(h, h->nev++), s); h->prev_fused = false; }
         ++h->acc_launches;
         ++h->acc_residual_launches;
         h->direct_ran = h->direct;
+        if (update_map) {
+            h->prev_fused = false;
+            std::string err;
+            int rc = h->map.sync_counters(s, err);  // also a sync: the caller observes a finished insert
+            if (rc) return fail(h, rc, err);
+            rc = check_stall(h);
+            if (rc) return rc;
+            uint32_t ovf = 0;
+            LK_CUDA(h, cudaMemcpy(&ovf, h->map.counters + 2, 4, cudaMemcpyDeviceToHost));
+            if (ovf) return fail(h, LK_ERR_CAPACITY, "map pools exhausted during UpdateVoxelMap (raise lk_map_reserve)");
+        }
         return LK_OK;
     }
     h->prev_fused = false;
@@ -1012,6 +1069,10 @@ int lk_batch_fetch(lk_handle h, lk_state* x_out, double* P_out, lk_stream_clock*
     }
     LK_CUDA(h, cudaStreamSynchronize(s));
     LK_CUDA(h, cudaGetLastError());
+    {
+        const int rc = check_stall(h);
+        if (rc) return rc;
+    }
     const char* ho = (const char*)h->h_small_out.p;
     if (x_out) std::memcpy(x_out, ho, (size_t)batch * sizeof(lk_state));
     if (P_out) std::memcpy(P_out, ho + h->out_off_P, (size_t)batch * 900 * 8);

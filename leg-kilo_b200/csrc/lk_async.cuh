@@ -5,6 +5,17 @@
 
 namespace lk {
 
+// Watchdog notes of this translation unit's kernels: a wait that never completes is bounded, leaves a code here and
+// lets the kernel finish (with garbage), so that a broken invariant shows up as an error instead of a hung device.
+//   [0] first code (1 mbarrier wait, 2 root-slot publication, 3 octree descent, 4 root-table probe) [1] block [2] thread [3] detail
+static __device__ uint32_t lk_stall_note[8];
+__device__ __forceinline__ void stall_note(uint32_t code, uint32_t detail) {
+    if (atomicCAS(&lk_stall_note[0], 0u, code) == 0u) {
+        lk_stall_note[1] = blockIdx.x; lk_stall_note[2] = threadIdx.x; lk_stall_note[3] = detail;
+        __threadfence();
+    }
+}
+
 // ---- mbarrier / bulk-copy primitives (PTX) ----------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -14,15 +25,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "LK_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra LK_DONE_%=;\n\t"
-        "bra LK_WAIT_%=;\n\t"
-        "LK_DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+        if (spins > (1u << 24)) {  // seconds: a bulk copy that never arrives (see lk_stall_note)
+            stall_note(1u, parity);
+            return;
+        }
+    }
 }
 // 1-D TMA bulk copy global -> shared::cta; size multiple of 16, both addresses 16-B aligned.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {

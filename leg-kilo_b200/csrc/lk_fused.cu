@@ -21,6 +21,7 @@
 // scan's blocks become resident and run their prologue (filter load, point prefetch) while this scan's
 // last blocks drain; everything that could collide with the previous launch (flagged rows, outputs) sits
 // behind griddepcontrol.wait.
+#include "lk_insert.cuh"
 #include "lk_kernels.h"
 #include "lk_obs.cuh"
 #include "lk_pass.cuh"
@@ -59,8 +60,14 @@ struct FusedSmem {
     } u;
 };
 
+// with the map insert inside: the plane-fit staging tiles of the warps, with their own mbarriers (initialised once)
+struct FusedSmemIns {
+    FusedSmem base;
+    WarpTile wt[WARPS];
+};
+
 static_assert(sizeof(PredictScratch) <= sizeof(((CachedPassSmem<BLOCK>*)0)->tile), "predict scratch must not reach the mbarriers");
-static_assert(sizeof(FusedSmem) <= 227 * 1024, "one block per SM");
+static_assert(sizeof(FusedSmemIns) <= 227 * 1024, "one block per SM");
 
 // KILO.cc:110-115: covariance with dt since the last UPDATE, state with dt since the last PREDICT; F is built
 // from the pre-propagation state. Out of line: a scan-at-once call (bucket time == both clocks) never gets here.
@@ -101,7 +108,19 @@ __device__ __noinline__ void fused_drain_queue(FusedSmem* sm, const FusedArgs& a
 template <bool INL> struct InlineSel { typedef FusedInline type; };
 template <> struct InlineSel<false> { typedef FusedNoInline type; };
 
-template <bool OBS, bool INL>
+// A grid-wide barrier out of the flagged-row all-reduce (every block contributes a zero row): the block's earlier global
+// writes are fenced first, and what the other blocks wrote is read through L2 afterwards (ld.global.cg / TMA).
+__device__ __forceinline__ void grid_sync(const FusedArgs& a, uint32_t& sync_idx) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x < 32) (void)ll_allreduce(a.ll, sync_idx & 1u, a.epoch + sync_idx, blockIdx.x, gridDim.x, 0.0, (int)threadIdx.x);
+    ++sync_idx;
+    __syncthreads();
+}
+
+// OBS: an inertial / kinematic queue is drained before every bucket. INL: the small inputs ride in the parameter block.
+// INS: UpdateVoxelMap runs inside the kernel after every bucket (KILO.cc:231): the map is then read through L2.
+template <bool OBS, bool INL, bool INS>
 __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__ FusedArgs a,
                                                          const __grid_constant__ typename InlineSel<INL>::type inl) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -129,11 +148,19 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
         if (tid < 36) sm->f.x[tid] = xin[tid];
         if (tid < 2) sm->clk[tid] = cin[tid];
     }
-    cached_pass_init<BLOCK>(&sm->u.pass);
+    if constexpr (INS) {
+        WarpTile* wt = reinterpret_cast<FusedSmemIns*>(smem_raw)->wt + warp;
+        if (lane == 0) {
+            mbar_init(&wt->bar, 1);
+            wt->phase = 0;
+        }
+    }
+    cached_pass_init<BLOCK>(&sm->u.pass);  // mbarrier init fence + block barrier
     FT(1);
     uint32_t n_eff_total = 0;
     uint32_t phase = 0;
-    uint32_t it_global = 0;
+    uint32_t it_global = 0;  // index of the next grid-wide exchange (all-reduce or barrier): tag and buffer parity
+    uint32_t cslot = 0;      // which of the two "touched roots" counters the current bucket uses (INS)
     uint32_t mi = 0;  // next inertial / kinematic sample
     bool dep_waited = false;
 
@@ -167,7 +194,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[i] = 0.0;
             if (!a.lane_cache && lc.have == 2) lc.have = 1;
-            cached_points_pass<BLOCK>(&sm->u.pass, phase, my_count, sm->sc, a.mv, a.g, acc, lc, pre);
+            cached_points_pass<BLOCK, INS>(&sm->u.pass, phase, my_count, sm->sc, a.mv, a.g, acc, lc, pre);
             const double tot = warp_transpose_sum(acc, lane);
             sm->slice[warp * 32 + lane] = tot;
             __syncthreads();
@@ -191,22 +218,57 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
             if (n > 0) {
                 updated = true;
                 if (tid == 0) sm->clk[1] = in.t_bucket;  // KILO.cc:212
-                if (last) cov_pending = more_steps || blockIdx.x == 0;
+                if (last) cov_pending = INS || more_steps || blockIdx.x == 0;  // the insert needs the updated covariance in every block
             }
             n_last = n;
         }
         n_eff_total += n_last;
-        // 4) re-projection with the updated state (KILO.cc:216-224)
-        if ((uint32_t)tid < my_count) {
-            const double* X = sm->f.x;
-            float4 o;
-            o.x = (float)(X[0] * lc.pix + X[1] * lc.piy + X[2] * lc.piz + X[9]);
-            o.y = (float)(X[3] * lc.pix + X[4] * lc.piy + X[5] * lc.piz + X[10]);
-            o.z = (float)(X[6] * lc.pix + X[7] * lc.piy + X[8] * lc.piz + X[11]);
-            o.w = updated ? 255.0f : 0.0f;
-            a.world[my_start + tid] = o;
+        if constexpr (!INS) {
+            // 4) re-projection with the updated state (KILO.cc:216-224)
+            if ((uint32_t)tid < my_count) {
+                const double* X = sm->f.x;
+                float4 o;
+                o.x = (float)(X[0] * lc.pix + X[1] * lc.piy + X[2] * lc.piz + X[9]);
+                o.y = (float)(X[3] * lc.pix + X[4] * lc.piy + X[5] * lc.piz + X[10]);
+                o.z = (float)(X[6] * lc.pix + X[7] * lc.piy + X[8] * lc.piz + X[11]);
+                o.w = updated ? 255.0f : 0.0f;
+                a.world[my_start + tid] = o;
+            }
+            if (cov_pending) block_cov_update<BLOCK>(&sm->f);
+        } else {
+            // 4') re-projection AND map insert with the updated state and covariance (KILO.cc:216-231). Phase 1, the blocks
+            //     that hold the bucket's points: pointWithVar, world cloud, find-or-create of the root voxel.
+            if (cov_pending) block_cov_update<BLOCK>(&sm->f);
+            __syncthreads();
+            scan_const_from(&sm->f, &sm->sc);
+            __syncthreads();
+            MapDev md = a.md;
+            const uint32_t n_bucket = in.pt_end - in.pt_begin;
+            if ((uint32_t)tid < my_count) {
+                // (without an update the reference inserts the point as the residual loop left it, KILO.cc:127-140, :215: the
+                // same formulas at the unchanged state)
+                DevPoint p;
+                make_insert_point(lc.pix, lc.piy, lc.piz, lc.pbx, lc.pby, lc.pbz, sm->sc, a.g, p);
+                const uint32_t li = my_start + tid - in.pt_begin;
+                a.ipts[li] = p;
+                float4 o;
+                o.x = (float)p.pw[0]; o.y = (float)p.pw[1]; o.z = (float)p.pw[2];
+                o.w = updated ? 255.0f : 0.0f;
+                a.world[my_start + tid] = o;
+                a.iroot[li] = insert_register_point(md, a.g, p, a.pend, a.touched, &a.ins_counters[cslot]);
+            }
+            grid_sync(a, it_global);
+            // Phase 2, every warp of every block: one touched root at a time, its points in index order
+            {
+                WarpTile* wt = reinterpret_cast<FusedSmemIns*>(smem_raw)->wt + warp;
+                const uint32_t n_touched = __ldcg(&a.ins_counters[cslot]);
+                if (blockIdx.x == 0 && tid == 0) a.ins_counters[cslot ^ 1u] = 0;  // the next bucket's counter
+                for (uint32_t t = blockIdx.x * (uint32_t)WARPS + (uint32_t)warp; t < n_touched; t += gridDim.x * (uint32_t)WARPS)
+                    warp_insert_root_scan(md, a.g, wt, __ldcg(&a.touched[t]), a.iroot, a.ipts, n_bucket, a.pend, lane);
+                cslot ^= 1u;
+            }
+            grid_sync(a, it_global);
         }
-        if (cov_pending) block_cov_update<BLOCK>(&sm->f);
     }
     FT(30);
     if (blockIdx.x == 0) {
@@ -220,14 +282,15 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
     FT(31);
 }
 
-template <bool OBS, bool INL>
+template <bool OBS, bool INL, bool INS>
 cudaError_t launch_one(const FusedArgs& a, const FusedInline* inl, uint32_t grid, cudaStream_t s, int mode) {
-    auto kern = k_scan_fused<OBS, INL>;
+    auto kern = k_scan_fused<OBS, INL, INS>;
+    constexpr size_t SMEM = INS ? sizeof(FusedSmemIns) : sizeof(FusedSmem);
     static bool attr[64];
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
         if (e != cudaSuccess) return e;
         attr[dev] = true;
     }
@@ -237,12 +300,12 @@ cudaError_t launch_one(const FusedArgs& a, const FusedInline* inl, uint32_t grid
     else { local_inl.unused = 0; ip = &local_inl; }
     if (mode == FUSED_LAUNCH_COOPERATIVE) {
         void* params[] = {(void*)&a, (void*)ip};
-        return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(BLOCK), params, sizeof(FusedSmem), s);
+        return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(BLOCK), params, SMEM, s);
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(BLOCK);
-    cfg.dynamicSmemBytes = sizeof(FusedSmem);
+    cfg.dynamicSmemBytes = SMEM;
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -255,6 +318,16 @@ cudaError_t launch_one(const FusedArgs& a, const FusedInline* inl, uint32_t grid
 }  // namespace
 
 size_t fused_smem_bytes() { return sizeof(FusedSmem); }
+
+// read and clear this translation unit's watchdog note (lk_async.cuh)
+int fused_read_stall(uint32_t out[8]) {
+    if (cudaMemcpyFromSymbol(out, lk_stall_note, 32) != cudaSuccess) return -1;
+    if (out[0]) {
+        const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cudaMemcpyToSymbol(lk_stall_note, z, 32);
+    }
+    return 0;
+}
 
 int fused_max_blocks(int device) {
     static int cached[64];
@@ -275,8 +348,12 @@ int fused_max_blocks(int device) {
 // multi-process caveat and the cooperative knob).
 cudaError_t launch_scan_fused(const FusedArgs& a, const FusedInline* inl, uint32_t grid, cudaStream_t s, int mode) {
     const bool obs = a.n_meas > 0;
-    if (obs) return inl ? launch_one<true, true>(a, inl, grid, s, mode) : launch_one<true, false>(a, inl, grid, s, mode);
-    return inl ? launch_one<false, true>(a, inl, grid, s, mode) : launch_one<false, false>(a, inl, grid, s, mode);
+    if (a.insert) {  // streaming with map insertion: never with inline inputs
+        if (inl) return cudaErrorInvalidValue;
+        return obs ? launch_one<true, false, true>(a, inl, grid, s, mode) : launch_one<false, false, true>(a, inl, grid, s, mode);
+    }
+    if (obs) return inl ? launch_one<true, true, false>(a, inl, grid, s, mode) : launch_one<true, false, false>(a, inl, grid, s, mode);
+    return inl ? launch_one<false, true, false>(a, inl, grid, s, mode) : launch_one<false, false, false>(a, inl, grid, s, mode);
 }
 
 }  // namespace lk

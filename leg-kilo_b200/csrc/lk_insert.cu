@@ -15,7 +15,7 @@
 // stores the re-projected world point (KILO.cc:216-224), so a bucket costs two launches instead of six.
 #include "lk_kernels.h"
 #include "lk_mapdev.h"
-#include "lk_octree.cuh"
+#include "lk_insert.cuh"
 
 namespace lk {
 
@@ -41,40 +41,6 @@ struct InsertArgs {
     uint32_t cslot;      // which of the two n_touched counters this bucket uses (small-bucket path)
 };
 
-__device__ __forceinline__ int hash_find_or_create(MapDev& md, const Globals& g, int kx, int ky, int kz) {
-    uint32_t i = hash_key(kx, ky, kz) & md.hash_mask;
-    for (uint32_t probe = 0; probe <= md.hash_mask; ++probe) {
-        int* nodep = &md.slots[i].node;
-        int node = *(volatile int*)nodep;
-        if (node == -1) {
-            int old = atomicCAS(nodep, -1, -2);
-            if (old == -1) {
-                md.slots[i].kx = kx; md.slots[i].ky = ky; md.slots[i].kz = kz;
-                uint32_t nd = atomicAdd(md.n_nodes, 1u);
-                if (nd >= md.node_cap) {
-                    atomicOr(md.overflow, 1u);
-                    __threadfence();
-                    atomicExch(nodep, -3);  // poisoned slot: key present, no node
-                    return -1;
-                }
-                init_root_node(md, g, nd, kx, ky, kz);
-                atomicAdd(md.n_roots, 1u);
-                __threadfence();
-                atomicExch(nodep, (int)nd);
-                return (int)nd;
-            }
-            node = old;
-        }
-        while (node == -2) node = *(volatile int*)nodep;  // another thread is publishing this slot
-        __threadfence();
-        const int sx = *(volatile int*)&md.slots[i].kx, sy = *(volatile int*)&md.slots[i].ky, sz = *(volatile int*)&md.slots[i].kz;
-        if (sx == kx && sy == ky && sz == kz) return node >= 0 ? node : -1;
-        i = (i + 1) & md.hash_mask;
-    }
-    atomicOr(md.overflow, 4u);
-    return -1;
-}
-
 // P1 — also the re-projection's covariance half (KILO.cc:225-228).
 __global__ void __launch_bounds__(256) k_insert_p1(const __grid_constant__ InsertArgs a) {
     __shared__ ScanConst s_sc;
@@ -91,45 +57,8 @@ __global__ void __launch_bounds__(256) k_insert_p1(const __grid_constant__ Inser
         const double pix = g.Re[0] * bx + g.Re[1] * by + g.Re[2] * bz0 + g.te[0];
         const double piy = g.Re[3] * bx + g.Re[4] * by + g.Re[5] * bz0 + g.te[1];
         const double piz = g.Re[6] * bx + g.Re[7] * by + g.Re[8] * bz0 + g.te[2];
-        const double* R = s_sc.R;
         DevPoint p;
-        p.pw[0] = R[0] * pix + R[1] * piy + R[2] * piz + s_sc.p[0];
-        p.pw[1] = R[3] * pix + R[4] * piy + R[5] * piz + s_sc.p[1];
-        p.pw[2] = R[6] * pix + R[7] * piy + R[8] * piz + s_sc.p[2];
-        // body covariance (calcBodyCov saw pb.z == 0 -> 1e-4)
-        const double bz = (bz0 == 0.0) ? 0.0001 : bz0;
-        const double r2 = bx * bx + by * by + bz * bz;
-        const float range = (float)sqrt(r2);
-        const double range2 = (double)range * (double)range;
-        const double inv = 1.0 / sqrt(r2);
-        const double ux = bx * inv, uy = by * inv, uz = bz * inv;
-        // M = R Re ; mu = M u
-        double M[9];
-        mat3_mul(R, g.Re, M);
-        const double mu[3] = {M[0] * ux + M[1] * uy + M[2] * uz, M[3] * ux + M[4] * uy + M[5] * uz, M[6] * ux + M[7] * uy + M[8] * uz};
-        double MMt[9];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) MMt[r * 3 + c] = M[r * 3] * M[c * 3] + M[r * 3 + 1] * M[c * 3 + 1] + M[r * 3 + 2] * M[c * 3 + 2];
-        const double ca = (double)g.rv - range2 * g.dv, cb = range2 * g.dv;
-        // G = R [pi]x ; G P_tt G^T
-        const double K[9] = {0, -piz, piy, piz, 0, -pix, -piy, pix, 0};
-        double G[9], GP[9];
-        mat3_mul(R, K, G);
-        const double* S = s_sc.Pth;
-        const double Pt[9] = {S[0], S[1], S[2], S[1], S[3], S[4], S[2], S[4], S[5]};
-        mat3_mul(G, Pt, GP);
-        const double* Sp = s_sc.Ppp;
-        const double Pp[9] = {Sp[0], Sp[1], Sp[2], Sp[1], Sp[3], Sp[4], Sp[2], Sp[4], Sp[5]};
-        const int ut[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-            const int r = ut[q][0], c = ut[q][1];
-            p.var[q] = ca * mu[r] * mu[c] + cb * MMt[r * 3 + c] + (GP[r * 3] * G[c * 3] + GP[r * 3 + 1] * G[c * 3 + 1] + GP[r * 3 + 2] * G[c * 3 + 2]) +
-                       Pp[r * 3 + c];
-        }
-        p.pad = 0.0;
+        make_insert_point(pix, piy, piz, bx, by, (bz0 == 0.0) ? 0.0001 : bz0, s_sc, g, p);  // calcBodyCov saw pb.z == 0 -> 1e-4
         const uint32_t li = cd.start + i - a.pt_base;
         a.ipts[li] = p;
         if (a.world) {
@@ -138,15 +67,7 @@ __global__ void __launch_bounds__(256) k_insert_p1(const __grid_constant__ Inser
             o.w = a.step[cd.scan].updated ? 255.0f : 0.0f;
             a.world[cd.start + i] = o;
         }
-        // voxelKeyFloor(point_w, (double)(float)voxel_size)  (voxel_map.cc:337,343)
-        const double vs = (double)g.voxel_f;
-        const int kx = (int)floor(p.pw[0] / vs), ky = (int)floor(p.pw[1] / vs), kz = (int)floor(p.pw[2] / vs);
-        const int root = hash_find_or_create(md, g, kx, ky, kz);
-        a.iroot[li] = root;
-        if (root >= 0) {
-            const int c = atomicAdd(&a.pend[root * 3], 1);
-            if (c == 0) a.touched[atomicAdd(&a.counters[a.cslot], 1u)] = (uint32_t)root;
-        }
+        a.iroot[li] = insert_register_point(md, g, p, a.pend, a.touched, &a.counters[a.cslot]);
     }
 }
 
@@ -220,23 +141,8 @@ __global__ void __launch_bounds__(128) k_insert_p4_scan(const __grid_constant__ 
     const uint32_t t = blockIdx.x * (blockDim.x >> 5) + warp;
     if (t >= a.counters[a.cslot]) return;
     const uint32_t root = a.touched[t];
-    const int cnt = a.pend[root * 3];
     MapDev md = a.md;
-    int done = 0;
-    for (uint32_t base = 0; base < a.n_pts && done < cnt; base += 32) {
-        const uint32_t j = base + (uint32_t)lane;
-        const int r = j < a.n_pts ? a.iroot[j] : -1;
-        uint32_t m = __ballot_sync(0xffffffffu, r == (int)root);
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const DevPoint p = a.ipts[base + (uint32_t)b];
-            warp_update_octo_tree(md, a.g, wt, root, p, lane);
-            ++done;
-        }
-    }
-    __syncwarp();
-    if (lane == 0) a.pend[root * 3] = 0;
+    warp_insert_root_scan(md, a.g, wt, root, a.iroot, a.ipts, a.n_pts, a.pend, lane);
 }
 
 }  // namespace

@@ -4,6 +4,7 @@
 
 #include "lk_device.cuh"
 #include "lk_llsync.cuh"
+#include "lk_plane.cuh"
 
 namespace lk {
 
@@ -122,7 +123,7 @@ struct FusedArgs {
     lk_stream_clock* clk;
     uint32_t* n_eff;
     LLView ll;       // flagged rows of the barrier-free all-reduce (lk_llsync.cuh)
-    uint32_t epoch;  // tag of this launch's first iteration; the launch uses epoch .. epoch + n_steps * iters - 1
+    uint32_t epoch;  // tag of this launch's first exchange; the launch uses epoch .. epoch + n_steps * (iters + 2) - 1
     int iters;
     int lane_cache;  // keep per-lane lookups / staged records across the iterations of a bucket
     int slim_p;        // blocks other than 0 load only P[:, 0:6] (valid when the scan has one bucket, no queue, no predict)
@@ -134,10 +135,19 @@ struct FusedArgs {
     lk_eskf_cfg ecfg;
     unsigned long long* trace;  // optional: 32 %globaltimer stamps per block
     Globals g;
+    // in-kernel UpdateVoxelMap after every bucket (streaming): the device map and the per-bucket scratch of lk_insert.cu
+    int insert;
+    MapDev md;
+    DevPoint* ipts;          // [largest bucket]
+    int* iroot;              // [largest bucket]
+    int* pend;               // [node_cap * 3]
+    uint32_t* touched;       // [largest bucket]
+    uint32_t* ins_counters;  // [2] touched-root counters used alternately by consecutive buckets (both zero at launch)
 };
 enum { FUSED_LAUNCH_PLAIN = 0, FUSED_LAUNCH_COOPERATIVE = 1, FUSED_LAUNCH_PDL = 2 };
 size_t fused_smem_bytes();
 int fused_max_blocks(int device);
+int fused_read_stall(uint32_t out[8]);  // watchdog note of the fused kernels (lk_async.cuh: lk_stall_note)
 // inl != null: the filter inputs and the step table ride in the parameter block
 cudaError_t launch_scan_fused(const FusedArgs& a, const FusedInline* inl, uint32_t grid, cudaStream_t s, int mode);
 

@@ -25,8 +25,14 @@ constexpr int LL_MAX_GROUPS = (LL_MAX_CHUNKS + LK_GROUP - 1) / LK_GROUP;
 struct LLView {
     ulonglong2* chunk_rows;  // [2][LL_MAX_CHUNKS][LL_ROW]
     ulonglong2* group_rows;  // [2][LL_MAX_GROUPS][LL_ROW]
+    uint32_t* stall;         // [8] watchdog record: [0] != 0 once a poll gave up | block | tag | first row | rows | lane
 };
-constexpr size_t LL_BYTES = (size_t)2 * (LL_MAX_CHUNKS + LL_MAX_GROUPS) * LL_ROW * sizeof(ulonglong2);
+constexpr size_t LL_ROWS_BYTES = (size_t)2 * (LL_MAX_CHUNKS + LL_MAX_GROUPS) * LL_ROW * sizeof(ulonglong2);
+constexpr size_t LL_BYTES = LL_ROWS_BYTES + 64;
+// A poll that sees nothing for this many rounds (seconds) gives up, records who waited for what and lets the kernel run
+// to its end with garbage sums; the host then reports LK_ERR_CUDA instead of hanging. It means the blocks of the grid were
+// not all resident (another process holds SMs: see INTEGRATION.md "Sharing a device") — or a bug.
+constexpr uint32_t LL_SPIN_LIMIT = 1u << 23;
 
 __device__ __forceinline__ void ll_store(ulonglong2* p, double v, uint32_t tag) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(v);
@@ -41,11 +47,12 @@ __device__ __forceinline__ void ll_store(ulonglong2* p, double v, uint32_t tag) 
 // change once published within an epoch, so re-reading the ones that already matched is harmless). One full warp.
 template <int N>
 __device__ __forceinline__ double ll_sum_rows(const ulonglong2* rows, uint32_t r0, uint32_t n, uint32_t tag, int lane,
-                                              double first = 0.0, bool have_first = false) {
+                                              uint32_t* stall, double first = 0.0, bool have_first = false) {
     const ulonglong2* p = rows + (size_t)r0 * LL_ROW + lane;
     unsigned long long w0[N], w1[N];
     const unsigned long long want = ((unsigned long long)tag << 32);
     bool all;
+    uint32_t spins = 0;
     do {
 #pragma unroll
         for (int k = 0; k < N; ++k)
@@ -56,6 +63,15 @@ __device__ __forceinline__ double ll_sum_rows(const ulonglong2* rows, uint32_t r
         for (int k = 0; k < N; ++k)
             if ((uint32_t)k < n && !(have_first && k == 0))
                 all = all && ((w0[k] & 0xffffffff00000000ull) == want) && ((w1[k] & 0xffffffff00000000ull) == want);
+        if (!all && ((++spins & 0xfffu) == 0u)) {  // watchdog, off the fast path
+            if (spins >= LL_SPIN_LIMIT || *reinterpret_cast<volatile uint32_t*>(stall) != 0u) {
+                if (atomicCAS(stall, 0u, 1u) == 0u) {
+                    stall[1] = blockIdx.x; stall[2] = tag; stall[3] = r0; stall[4] = n; stall[5] = (uint32_t)lane;
+                    __threadfence();
+                }
+                break;
+            }
+        }
     } while (!all);
     double s = 0.0;
 #pragma unroll
@@ -80,13 +96,13 @@ __device__ __forceinline__ double ll_allreduce(const LLView& ll, uint32_t parity
     if (b < n_chunks) {
         if ((b % LK_GROUP) == 0) {
             const uint32_t n = min((uint32_t)LK_GROUP, n_chunks - b);
-            const double s = ll_sum_rows<LK_GROUP>(crows, b, n, tag, lane, v, true);
+            const double s = ll_sum_rows<LK_GROUP>(crows, b, n, tag, lane, ll.stall, v, true);
             ll_store(grows + (size_t)(b / LK_GROUP) * LL_ROW + lane, s, tag);
         } else {
             ll_store(crows + (size_t)b * LL_ROW + lane, v, tag);
         }
     }
-    return ll_sum_rows<LL_MAX_GROUPS>(grows, 0, n_groups, tag, lane);
+    return ll_sum_rows<LL_MAX_GROUPS>(grows, 0, n_groups, tag, lane, ll.stall);
 }
 
 }  // namespace lk

@@ -306,8 +306,12 @@ __device__ inline void warp_append(MapDev& md, const Globals& g, uint32_t nd, co
 // VoxelOctoTree::UpdateOctoTree(pv) starting at root `nd` (voxel_map.cc:185-241). Warp-wide.
 __device__ inline void warp_update_octo_tree(MapDev& md, const Globals& g, WarpTile* wt, uint32_t nd, const DevPoint& p,
                                              int lane) {
-    for (;;) {
+    for (int depth = 0;; ++depth) {
         __syncwarp();
+        if (depth > 8) {  // deeper than any max_layer: the tree is corrupt (see lk_stall_note)
+            stall_note(3u, nd);
+            return;
+        }
         const uint32_t flags = md.nodes[nd].flags;
         const int layer = (int)((flags >> LK_NODE_LAYER_SHIFT) & 0xffu);
         if (!(flags & LK_NODE_INIT_OCTO)) {

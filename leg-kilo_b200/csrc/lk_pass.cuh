@@ -88,13 +88,17 @@ __device__ __forceinline__ void pass_init(PassSmem<NTHREADS>* ps) {
 struct SlotPair {
     int4 a, b;
 };
+template <bool COH = false>
 __device__ __forceinline__ SlotPair load_pair(const HashSlot* __restrict__ slots, uint32_t i) {
     SlotPair p;
     const int4* q = reinterpret_cast<const int4*>(slots + (i & ~1u));
-    p.a = __ldg(q);
-    p.b = __ldg(q + 1);
+    p.a = COH ? __ldcg(q) : __ldg(q);
+    p.b = COH ? __ldcg(q + 1) : __ldg(q + 1);
     return p;
 }
+// A slot whose node is -2 / -3 is being published / was poisoned by an insert (lk_insert.cuh); both are negative, so
+// the probe treats them as "end of the chain" — the persistent kernel only probes between inserts, never during one.
+template <bool COH = false>
 __device__ __forceinline__ int resolve_pair(const HashSlot* __restrict__ slots, uint32_t mask, uint32_t i, SlotPair p,
                                             int kx, int ky, int kz) {
     // first step may start on the odd slot of its pair
@@ -105,8 +109,12 @@ __device__ __forceinline__ int resolve_pair(const HashSlot* __restrict__ slots, 
     if (p.b.w < 0) return -1;
     if (p.b.x == kx && p.b.y == ky && p.b.z == kz) return p.b.w;
     uint32_t j = ((i & ~1u) + 2) & mask;
-    for (;;) {
-        p = load_pair(slots, j);
+    for (uint32_t probes = 0;; ++probes) {
+        if (probes > mask) {  // walked the whole table without meeting an empty slot (see lk_stall_note)
+            stall_note(4u, i);
+            return -1;
+        }
+        p = load_pair<COH>(slots, j);
         if (p.a.w < 0) return -1;
         if (p.a.x == kx && p.a.y == ky && p.a.z == kz) return p.a.w;
         if (p.b.w < 0) return -1;
@@ -184,12 +192,13 @@ __device__ __forceinline__ bool fallback_pick(const PS* ps, uint32_t& fb_slot) {
     return threadIdx.x < n_fb;
 }
 
+template <bool COH = false>
 __device__ __forceinline__ bool eval_record(const MapNode* __restrict__ nodes, const PlaneRec& r, const PointCtx& pc,
                                             const ScanConst& sc, const Globals& g, Row& row) {
     double prob = 0.0;
     if (r.flags & LK_NODE_IS_PLANE) return eval_plane(r, pc, sc, g, false, prob, row);
     const uint32_t cmask = (r.flags >> LK_NODE_CHILDMASK_SHIFT) & 0xffu;
-    if (g.max_layer >= 1 && r.child_base >= 0 && cmask) return visit_subtree(nodes, r.child_base, cmask, &pc, &sc, &g, &prob, &row);
+    if (g.max_layer >= 1 && r.child_base >= 0 && cmask) return visit_subtree<COH>(nodes, r.child_base, cmask, &pc, &sc, &g, &prob, &row);
     return false;
 }
 
@@ -313,7 +322,7 @@ __device__ __forceinline__ void cached_pass_init(CachedPassSmem<NTHREADS>* ps) {
     __syncthreads();
 }
 
-template <int NTHREADS>
+template <int NTHREADS, bool COH = false>
 __device__ __forceinline__ void cached_points_pass(CachedPassSmem<NTHREADS>* ps, uint32_t& phase, uint32_t count,
                                                    const ScanConst& sc, const MapView& mv, const Globals& g,
                                                    double (&acc)[32], LaneCache& lc, float4 pre) {
@@ -352,17 +361,17 @@ __device__ __forceinline__ void cached_points_pass(CachedPassSmem<NTHREADS>* ps,
             near = lc.near;
             if (lc.nx != nx || lc.ny != ny || lc.nz != nz) {  // same home voxel, different neighbour: redo that lookup only
                 const uint32_t in = hash_key(nx, ny, nz) & mv.hash_mask;
-                near = (root >= 0 && differs) ? resolve_pair(mv.slots, mv.hash_mask, in, load_pair(mv.slots, in), nx, ny, nz) : -1;
+                near = (root >= 0 && differs) ? resolve_pair<COH>(mv.slots, mv.hash_mask, in, load_pair<COH>(mv.slots, in), nx, ny, nz) : -1;
                 gather_near = near >= 0;
             }
         } else {
             // both home pairs are read before either is inspected
             const uint32_t ih = hash_key(kx, ky, kz) & mv.hash_mask, in = hash_key(nx, ny, nz) & mv.hash_mask;
-            const SlotPair sh = load_pair(mv.slots, ih);
-            const SlotPair sn = load_pair(mv.slots, in);
-            root = resolve_pair(mv.slots, mv.hash_mask, ih, sh, kx, ky, kz);
+            const SlotPair sh = load_pair<COH>(mv.slots, ih);
+            const SlotPair sn = load_pair<COH>(mv.slots, in);
+            root = resolve_pair<COH>(mv.slots, mv.hash_mask, ih, sh, kx, ky, kz);
             // the reference only looks at the neighbour when the home voxel exists
-            near = (root >= 0 && differs) ? resolve_pair(mv.slots, mv.hash_mask, in, sn, nx, ny, nz) : -1;
+            near = (root >= 0 && differs) ? resolve_pair<COH>(mv.slots, mv.hash_mask, in, sn, nx, ny, nz) : -1;
             gather_home = root >= 0;
             gather_near = near >= 0;
         }
@@ -388,7 +397,7 @@ __device__ __forceinline__ void cached_points_pass(CachedPassSmem<NTHREADS>* ps,
     if (root >= 0) {
         PlaneRec r;
         plane_from_smem(home_slot, r);
-        ok = eval_record(mv.nodes, r, pc, sc, g, row);
+        ok = eval_record<COH>(mv.nodes, r, pc, sc, g, row);
     }
     fallback_list<NTHREADS>(ps, root >= 0 && !ok && near >= 0, pc, near, lane, warp);
     __syncthreads();
@@ -403,7 +412,7 @@ __device__ __forceinline__ void cached_points_pass(CachedPassSmem<NTHREADS>* ps,
         fc.pwx = f.pc[6]; fc.pwy = f.pc[7]; fc.pwz = f.pc[8]; fc.r2 = f.pc[9]; fc.range2 = f.pc[10];
         PlaneRec r;
         plane_from_smem(ps->tile[1] + (size_t)f.idx * TILE_STRIDE, r);
-        ok2 = eval_record(mv.nodes, r, fc, sc, g, row2);
+        ok2 = eval_record<COH>(mv.nodes, r, fc, sc, g, row2);
     }
     if (ok) accumulate_row(row, acc);
     if (ok2) accumulate_row(row2, acc);

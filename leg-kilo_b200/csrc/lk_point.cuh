@@ -19,12 +19,14 @@ struct PlaneRec {
     int child_base;
 };
 
-// 15 x 128-bit read-only loads cover the 232 bytes the path needs (lk_map_node).
+// 15 x 128-bit loads cover the 232 bytes the path needs (lk_map_node). COH = the map may be written by this very kernel
+// (persistent per-scan kernel with the map insert inside): read through L2 instead of the non-coherent path.
+template <bool COH = false>
 __device__ __forceinline__ void load_plane(const MapNode* __restrict__ nd, PlaneRec& r) {
     const double2* q = reinterpret_cast<const double2*>(nd);
     double2 v[15];
 #pragma unroll
-    for (int i = 0; i < 15; ++i) v[i] = __ldg(q + i);
+    for (int i = 0; i < 15; ++i) v[i] = COH ? __ldcg(q + i) : __ldg(q + i);
     r.c[0] = v[0].x; r.c[1] = v[0].y; r.c[2] = v[1].x;
     r.n[0] = v[1].y; r.n[1] = v[2].x; r.n[2] = v[2].y;
 #pragma unroll
@@ -131,6 +133,7 @@ __device__ __forceinline__ int map_find(const HashSlot* __restrict__ slots, uint
 // Rare path of build_single_residual (voxel_map.cc:412-424): the root is not a plane, so every
 // initialised plane among ALL children of non-plane nodes down to max_layer is a candidate and the
 // most probable one wins. Kept out of line so the common path does not carry its registers.
+template <bool COH = false>
 static __device__ __noinline__ bool visit_subtree(const MapNode* __restrict__ nodes, int child_base, uint32_t cmask,
                                            const PointCtx* pcp, const ScanConst* scp, const Globals* gp, double* probp,
                                            Row* rowp) {
@@ -152,7 +155,7 @@ static __device__ __noinline__ bool visit_subtree(const MapNode* __restrict__ no
         st_mask[sp - 1] = m & (m - 1);
         int layer = sp;  // children of a layer-(sp-1) node
         PlaneRec cr;
-        load_plane(nodes + st_base[sp - 1] + c, cr);
+        load_plane<COH>(nodes + st_base[sp - 1] + c, cr);
         if (cr.flags & LK_NODE_IS_PLANE) {
             if (eval_plane(cr, pc, sc, g, true, prob, row)) ok = true;
         } else if (layer < g.max_layer && sp < 4) {

@@ -1,0 +1,15 @@
+#!/bin/bash
+cd "$(dirname "$0")/.." && mkdir -p gpurun_out
+timeout -k 5 200 python -m pytest tests/test_gpu_map.py tests/test_gpu_filter.py -m gpu -x -q > gpurun_out/s15_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s15_pytest.log
+tail -4 gpurun_out/s15_pytest.log
+for wl in nclt_stream leg_fusion_stream; do
+timeout -k 5 120 python bench.py --workload $wl --steps 40 --warmup 5 > gpurun_out/s15_$wl.json 2> gpurun_out/s15_err.log
+python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/s15_$wl.json"))
+    print("$wl p50 %.3f ms mean %.3f p95 %.3f" % (d["value"], d["ms_per_step"], d["p95_ms"]), d["config"]["n_eff_mean"])
+except Exception as e: print("$wl failed", e)
+PY
+tail -2 gpurun_out/s15_err.log
+done
