@@ -264,7 +264,7 @@ def cpu_reference_run(wl, w, scan_ids, nthreads, gain_information=True):
     return sec, xo, Po, ne, int(offs[-1])
 
 
-def stream_run(cfgname, n_timed, n_warm, impl_ref, device=0):
+def stream_run(cfgname, n_timed, n_warm, impl_ref, device=0, params=()):
     """BASELINE configs[4]: 10 Hz stream of scans, ~50 time buckets each, inertial (nclt: only_imu_use) or
     kinematic+inertial (leg_fusion) queue interleaved, map updated after every bucket. One STEP = one scan through
     lk_process_scan with HOST buffers (this mode is end-to-end by nature). Returns per-scan wall ms and counters."""
@@ -296,6 +296,9 @@ def stream_run(cfgname, n_timed, n_warm, impl_ref, device=0):
             return xo, Po.reshape(1, 900), co, r["n_eff"]
     else:
         eng = Engine(cfg, device=device)
+        for kv in params:
+            k, v = kv.split("=")
+            eng.set_param(k, float(v))
         eng.map_build(pw, pb)
 
         def proc(x, P, clk, pts, offs, times, meas, t0):
@@ -322,7 +325,7 @@ def stream_latency(args):
     cfgname = "nclt" if args.workload == "nclt_stream" else "leg_fusion"
     K, W = max(args.steps, 8), max(args.warmup, 3)
     impl_ref = args.impl == "reference"
-    r = stream_run(cfgname, K, W, impl_ref, device=int(os.environ.get("LOCAL_RANK", "0")))
+    r = stream_run(cfgname, K, W, impl_ref, device=int(os.environ.get("LOCAL_RANK", "0")), params=args.param)
     lat = r["lat"]
     line = dict(metric="p50 per-scan latency of the streaming ESKF LiDAR update (10 Hz, ~50 buckets/scan, map updated per bucket)",
                 value=float(np.median(lat)), unit="ms", n_gpus=1, steps=K, warmup=W, ms_per_step=float(np.mean(lat)),
@@ -651,7 +654,7 @@ def main():
         # configs[4]: the streaming latency mode, end to end by nature (rank 0)
         if rank == 0 and B == 1 and not args.no_stream:
             eng.close()
-            sr = stream_run("nclt", max(args.stream_scans, 30), 5, False, device=local_rank)
+            sr = stream_run("nclt", max(args.stream_scans, 30), 5, False, device=local_rank, params=args.param)
             e2e["stream_p50_ms"] = float(np.median(sr["lat"]))
             e2e["stream"] = dict(workload="nclt_stream", baseline_config="configs[4]: NCLT-style 10 Hz stream, IMU observations, latency mode",
                                  scans=len(sr["lat"]), p50_ms=float(np.median(sr["lat"])), p95_ms=float(np.percentile(sr["lat"], 95)),

@@ -115,7 +115,8 @@ struct lk_context {
     int direct_io = 1, inline_in = 1, coop_launch = 0, pdl = 1, n_sms = 148, slim_p = 1;
     size_t h_off_clk = 0;  // offset of the staged clocks inside h_small_in
     int fast_insert = 1;  // update_map: two-launch insert for small buckets, re-projection folded into it
-    int fused_insert = 1;  // update_map of one scan with small buckets: UpdateVoxelMap inside the persistent kernel
+    int fused_insert = 0;  // 1 = update_map of one scan with small buckets: UpdateVoxelMap inside the persistent kernel (one
+                           // launch per scan; measured slower than the per-bucket kernels, see profiles/r2_summary.md)
     bool direct = false, direct_ran = false, inline_ok = false;
     const float4* direct_pts = nullptr;
     float4* direct_world = nullptr;

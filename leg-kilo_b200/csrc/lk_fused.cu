@@ -38,6 +38,8 @@ __device__ __forceinline__ unsigned long long gtime() {
     return t;
 }
 #define FT(slot) do { if (a.trace && threadIdx.x == 0 && (slot) < 32) a.trace[(size_t)blockIdx.x * 32 + (slot)] = gtime(); } while (0)
+// per-bucket stamps of the streaming variants (block 0, first 64 buckets, 8 stamps each, behind the per-block area)
+#define FTS(slot) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0 && k < 64) a.trace[(size_t)gridDim.x * 32 + (size_t)k * 8 + (slot)] = gtime(); } while (0)
 
 constexpr int BLOCK = FB;
 constexpr int WARPS = BLOCK / 32;
@@ -64,7 +66,20 @@ struct FusedSmem {
 struct FusedSmemIns {
     FusedSmem base;
     WarpTile wt[WARPS];
+    MapDev md;   // copies for the out-of-line insert phase
+    Globals g;
 };
+
+// Phase 2 of the in-kernel UpdateVoxelMap, out of line: the octree / plane-fit code then gets a register allocation of
+// its own (as in the stand-alone insert kernel) instead of spilling inside the persistent kernel's.
+__device__ __noinline__ void fused_insert_phase2(FusedSmemIns* si, const uint32_t* touched, const int* iroot, const DevPoint* ipts,
+                                                 int* pend, uint32_t n_touched, uint32_t n_bucket) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    MapDev md = si->md;
+    WarpTile* wt = si->wt + warp;
+    for (uint32_t t = blockIdx.x * (uint32_t)WARPS + (uint32_t)warp; t < n_touched; t += gridDim.x * (uint32_t)WARPS)
+        warp_insert_root_scan(md, si->g, wt, __ldcg(&touched[t]), iroot, ipts, n_bucket, pend, lane);
+}
 
 static_assert(sizeof(PredictScratch) <= sizeof(((CachedPassSmem<BLOCK>*)0)->tile), "predict scratch must not reach the mbarriers");
 static_assert(sizeof(FusedSmemIns) <= 227 * 1024, "one block per SM");
@@ -149,11 +164,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
         if (tid < 2) sm->clk[tid] = cin[tid];
     }
     if constexpr (INS) {
-        WarpTile* wt = reinterpret_cast<FusedSmemIns*>(smem_raw)->wt + warp;
+        FusedSmemIns* si = reinterpret_cast<FusedSmemIns*>(smem_raw);
+        WarpTile* wt = si->wt + warp;
         if (lane == 0) {
             mbar_init(&wt->bar, 1);
             wt->phase = 0;
         }
+        if (tid == 0) si->md = a.md;
+        if (tid < (int)(sizeof(Globals) / 4)) reinterpret_cast<uint32_t*>(&si->g)[tid] = reinterpret_cast<const uint32_t*>(&a.g)[tid];
     }
     cached_pass_init<BLOCK>(&sm->u.pass);  // mbarrier init fence + block barrier
     FT(1);
@@ -176,11 +194,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
         const uint32_t my_count = blockIdx.x < n_chunks ? min((uint32_t)BLOCK, in.pt_end - my_start) : 0u;
         float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
         if ((uint32_t)tid < my_count) pre = __ldg(a.pts + my_start + tid);
+        FTS(0);
         if constexpr (OBS) fused_drain_queue(sm, a, mi, in.t_bucket);
+        FTS(1);
         const double dtc = in.t_bucket - sm->clk[1];
         const double dt = in.t_bucket - sm->clk[0];
         if (dtc != 0.0 || dt != 0.0) fused_predict(sm, a.Q, dtc, dt);
         if (tid == 0) sm->clk[0] = in.t_bucket;
+        FTS(2);
         bool updated = false, cov_pending = false;
         uint32_t n_last = 0;
         LaneCache lc;
@@ -199,6 +220,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
             sm->slice[warp * 32 + lane] = tot;
             __syncthreads();
             FT(2 + it_global * 4);
+            if (it == 0) FTS(3);
             // 2) all-reduce of the block rows (warp 0), no barrier
             if (warp == 0) {
                 double v = 0.0;
@@ -210,6 +232,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
             dep_waited = true;
             __syncthreads();
             FT(3 + it_global * 4);
+            if (it == 0) FTS(4);
             // 3) every block solves redundantly (eskf.cc:91-113); the covariance update of the last iteration is
             //    deferred behind the re-projection, and skipped where nobody reads the result
             const bool last = it == a.iters - 1;
@@ -223,6 +246,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
             n_last = n;
         }
         n_eff_total += n_last;
+        FTS(5);
         if constexpr (!INS) {
             // 4) re-projection with the updated state (KILO.cc:216-224)
             if ((uint32_t)tid < my_count) {
@@ -258,16 +282,16 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
                 a.iroot[li] = insert_register_point(md, a.g, p, a.pend, a.touched, &a.ins_counters[cslot]);
             }
             grid_sync(a, it_global);
+            FTS(6);
             // Phase 2, every warp of every block: one touched root at a time, its points in index order
             {
-                WarpTile* wt = reinterpret_cast<FusedSmemIns*>(smem_raw)->wt + warp;
                 const uint32_t n_touched = __ldcg(&a.ins_counters[cslot]);
                 if (blockIdx.x == 0 && tid == 0) a.ins_counters[cslot ^ 1u] = 0;  // the next bucket's counter
-                for (uint32_t t = blockIdx.x * (uint32_t)WARPS + (uint32_t)warp; t < n_touched; t += gridDim.x * (uint32_t)WARPS)
-                    warp_insert_root_scan(md, a.g, wt, __ldcg(&a.touched[t]), a.iroot, a.ipts, n_bucket, a.pend, lane);
+                fused_insert_phase2(reinterpret_cast<FusedSmemIns*>(smem_raw), a.touched, a.iroot, a.ipts, a.pend, n_touched, n_bucket);
                 cslot ^= 1u;
             }
             grid_sync(a, it_global);
+            FTS(7);
         }
     }
     FT(30);

@@ -81,20 +81,32 @@ __device__ inline bool warp_gauss_jordan(double* Aug, int m, int ncols, int lane
 // K = PHT S^-1, delta = K z, x (+)= delta, P -= K (H P) with a dense m x 30 H in s->H, innovation
 // s->z and noise s->r (eskf.cc:137-145; also used for the IMU-only update, whose closed form
 // eskf.cc:127-134 is this with H = [0 I6 0 I6 0]). All threads.
+// imu_rows: the first 6 rows of H are the inertial rows [0 I6 0 I6 0] (ones at columns 9 + a and 18 + a): their products
+// are two-term sums. Dropping the structural zeros keeps every sum bit-identical to the dense loops (same order, exact zeros).
 template <int NTHREADS>
-__device__ inline void block_update_dense(BlockFilter* f, ObsScratch* s, int m) {
+__device__ inline void block_update_dense(BlockFilter* f, ObsScratch* s, int m, bool imu_rows = false) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // PHT = P H^T (30 x m) and HP = H P (m x 30) into the augmented matrix
     for (int e = tid; e < 30 * m; e += NTHREADS) {
         const int i = e / m, a = e % m;
         double v = 0.0;
-        for (int k = 0; k < 30; ++k) v += f->P[i * 30 + k] * s->H[a * 30 + k];
+        if (imu_rows && a < 6) {
+            v += f->P[i * 30 + 9 + a];
+            v += f->P[i * 30 + 18 + a];
+        } else {
+            for (int k = 0; k < 30; ++k) v += f->P[i * 30 + k] * s->H[a * 30 + k];
+        }
         s->PHT[i * OBS_MAX_M + a] = v;
     }
     for (int e = tid; e < m * 30; e += NTHREADS) {
         const int a = e / 30, j = e % 30;
         double v = 0.0;
-        for (int k = 0; k < 30; ++k) v += s->H[a * 30 + k] * f->P[k * 30 + j];
+        if (imu_rows && a < 6) {
+            v += f->P[(9 + a) * 30 + j];
+            v += f->P[(18 + a) * 30 + j];
+        } else {
+            for (int k = 0; k < 30; ++k) v += s->H[a * 30 + k] * f->P[k * 30 + j];
+        }
         s->Aug[a * OBS_AUG_COLS + m + 1 + j] = v;
     }
     __syncthreads();
@@ -102,7 +114,12 @@ __device__ inline void block_update_dense(BlockFilter* f, ObsScratch* s, int m) 
     for (int e = tid; e < m * m; e += NTHREADS) {
         const int a = e / m, b = e % m;
         double v = (a == b) ? s->r[a] : 0.0;
-        for (int k = 0; k < 30; ++k) v += s->H[a * 30 + k] * s->PHT[k * OBS_MAX_M + b];
+        if (imu_rows && a < 6) {
+            v += s->PHT[(9 + a) * OBS_MAX_M + b];
+            v += s->PHT[(18 + a) * OBS_MAX_M + b];
+        } else {
+            for (int k = 0; k < 30; ++k) v += s->H[a * 30 + k] * s->PHT[k * OBS_MAX_M + b];
+        }
         s->Aug[a * OBS_AUG_COLS + b] = v;
     }
     if (tid < m) s->Aug[tid * OBS_AUG_COLS + m] = s->z[tid];
@@ -153,7 +170,7 @@ __device__ inline void block_obs_imu(BlockFilter* f, ObsScratch* s, const lk_imu
         s->r[tid] = (tid < 2) ? cfg->imu_acc_meas_noise : (tid == 2 ? cfg->imu_acc_z_meas_noise : cfg->imu_gyr_meas_noise);
     }
     __syncthreads();
-    block_update_dense<NTHREADS>(f, s, 6);
+    block_update_dense<NTHREADS>(f, s, 6, true);
 }
 
 // KILO::predictUpdateKinImu's observation (KILO.cc:268-310).
@@ -203,7 +220,7 @@ __device__ inline void block_obs_kinimu(BlockFilter* f, ObsScratch* s, const lk_
         }
     }
     __syncthreads();
-    block_update_dense<NTHREADS>(f, s, m);
+    block_update_dense<NTHREADS>(f, s, m, true);
 }
 
 }  // namespace lk

@@ -34,23 +34,55 @@ __device__ inline void build_F(double* F, const double* x, double dt) {
     __syncthreads();
 }
 
-// P <- F P F^T + dt^2 Q  (eskf.cc:86-87). F, T in shared; P in global (L2-resident, 7.2 KB).
+// The structural non-zeros of getFx's F (eskf.cc:72-81), row by row, columns ascending: rows 0-2 (theta) hold Exp(-w dt) and
+// dt on imu_w; rows 3-5 (pos) 1 and dt on vel; rows 6-8 (vel) -dt R [a]x, 1, dt on grav, dt R on imu_a; every other row is a
+// row of the identity. Skipping the structural zeros leaves every sum bit-identical to the dense product (the terms that
+// remain are added in the same ascending order; the dropped ones are exact zeros).
+__device__ __forceinline__ int f_row_pattern(int r, int (&col)[8]) {
+    if (r < 3) { col[0] = 0; col[1] = 1; col[2] = 2; col[3] = 21 + r; return 4; }
+    if (r < 6) { col[0] = r; col[1] = r + 3; return 2; }
+    if (r < 9) { col[0] = 0; col[1] = 1; col[2] = 2; col[3] = r; col[4] = r + 9; col[5] = 18; col[6] = 19; col[7] = 20; return 8; }
+    col[0] = r;
+    return 1;
+}
+
+// P <- F P F^T + dt^2 Q  (eskf.cc:86-87). F, T, Ps in shared memory; P wherever the caller keeps it.
 __device__ inline void cov_predict(double* Pg, const double* F, double* T, double* Ps, const double* Q, double dt) {
     const int tid = threadIdx.x;
     for (int e = tid; e < 900; e += FB) Ps[e] = Pg[e];
     __syncthreads();
+    // T = F P: only rows 0..8 of F differ from the identity
     for (int e = tid; e < 900; e += FB) {
-        int i = e / 30, j = e % 30;
-        double s = 0.0;
-        for (int k = 0; k < 30; ++k) s += F[i * 30 + k] * Ps[k * 30 + j];
+        const int i = e / 30, j = e % 30;
+        double s;
+        if (i >= 9) {
+            s = Ps[e];
+        } else {
+            int col[8];
+            const int n = f_row_pattern(i, col);
+            s = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q < n) s += F[i * 30 + col[q]] * Ps[col[q] * 30 + j];
+        }
         T[e] = s;
     }
     __syncthreads();
     const double dt2 = dt * dt;
+    // P = T F^T + dt^2 Q: column j of the product is a sparse combination for j < 9, a copy otherwise
     for (int e = tid; e < 900; e += FB) {
-        int i = e / 30, j = e % 30;
-        double s = 0.0;
-        for (int k = 0; k < 30; ++k) s += T[i * 30 + k] * F[j * 30 + k];
+        const int i = e / 30, j = e % 30;
+        double s;
+        if (j >= 9) {
+            s = T[e];
+        } else {
+            int col[8];
+            const int n = f_row_pattern(j, col);
+            s = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q < n) s += T[i * 30 + col[q]] * F[j * 30 + col[q]];
+        }
         Pg[e] = s + dt2 * Q[e];
     }
     __syncthreads();

@@ -61,10 +61,13 @@ def test_inertial_and_kinematic_observations(kind):
     assert cg.tobytes() == co.tobytes()
 
 
-@pytest.mark.parametrize("kind,update_map", [("imu", False), ("kin", False), ("imu", True), ("kin", True)])
+@pytest.mark.parametrize("kind,update_map", [("imu", False), ("kin", False), ("imu", True), ("kin", True), ("imu", "in-kernel"), ("kin", "in-kernel")])
 def test_process_scan_with_interleaved_queue(kind, update_map):
     """KILO::process's second lambda: ~50 buckets, every sample with stamp < bucket time applied first
-    (KILO.cc:379-390). update_map=False runs the fused persistent kernel, True the multi-kernel path."""
+    (KILO.cc:379-390). update_map=False runs the fused persistent kernel, True the per-bucket kernels, "in-kernel" the
+    persistent kernel with UpdateVoxelMap inside (queue drain, predict, update and insert of all buckets in ONE launch)."""
+    in_kernel = update_map == "in-kernel"
+    update_map = bool(update_map)
     cfg, blob, scans = scenes.box_scene(batch=1, streaming=True, stream0=1100)
     pts, offs, times = synth.bucketize(scans[0], begin_time=20.0)
     x0 = tp._moving_state(); P0 = abi.init_cov(1)
@@ -76,6 +79,7 @@ def test_process_scan_with_interleaved_queue(kind, update_map):
     ro = o.process_scan(20.0, pts, imu=meas if kind == "imu" else None, kin=meas if kind == "kin" else None)
     xo, Po, _, co = o.get_filter()
     eng = Engine(cfg); eng.map_upload(blob)
+    eng.set_param("fused_insert", 1 if in_kernel else 0)
     out = eng.process_scan(x0, P0, Q, clk, pts, offs, times, imu=meas if kind == "imu" else None,
                            kin=meas if kind == "kin" else None, gravity=9.81, acc_norm=9.79, update_map=update_map)
     assert out["n_consumed"] == ro["n_consumed"] > 30 and out["n_eff"] == ro["n_eff"] > 0

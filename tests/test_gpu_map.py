@@ -65,7 +65,7 @@ def test_map_upload_download_roundtrip():
     assert st["planes"] == 576
 
 
-def _stream_case(streaming, iters=1, stream0=700, empty_map=False, n_scans=2, fast_insert=1, check_world=False):
+def _stream_case(streaming, iters=1, stream0=700, empty_map=False, n_scans=2, fast_insert=1, check_world=False, fused_insert=0):
     import test_gpu_parity as tp
     cfg, blob, scans = scenes.box_scene(batch=2, streaming=streaming, stream0=stream0)
     x0 = tp._moving_state() if streaming else abi.default_states(1)
@@ -74,6 +74,7 @@ def _stream_case(streaming, iters=1, stream0=700, empty_map=False, n_scans=2, fa
     o = lko.Oracle(cfg)
     eng = Engine(cfg)
     eng.set_param("fast_insert", fast_insert)
+    eng.set_param("fused_insert", fused_insert)
     if not empty_map:
         o.map_import(blob)
         eng.map_upload(blob)
@@ -106,13 +107,15 @@ def test_update_map_scan_at_once():
     assert st["planes"] > 3000
 
 
-@pytest.mark.parametrize("fast_insert", [1, 0])
+@pytest.mark.parametrize("insert", ["two-launch", "slice-and-sort", "in-kernel"])
 @pytest.mark.parametrize("iters", [1, 2])
-def test_update_map_streaming(iters, fast_insert):
+def test_update_map_streaming(iters, insert):
     """~50 buckets per scan, map mutated between buckets (refits every 6th insertion per leaf, freezes
-    at 50 points, new roots / octants on demand) — the full reference loop on the device, through both insert
-    paths (two launches per small bucket / the general slice-and-sort path)."""
-    st = _stream_case(streaming=True, iters=iters, fast_insert=fast_insert, check_world=True)
+    at 50 points, new roots / octants on demand) — the full reference loop on the device, through all three insert
+    paths: two launches per small bucket, the general slice-and-sort path, and UpdateVoxelMap inside the persistent
+    per-scan kernel (one launch per scan, grid barriers between the phases, map read through L2)."""
+    st = _stream_case(streaming=True, iters=iters, fast_insert=0 if insert == "slice-and-sort" else 1, check_world=True,
+                      fused_insert=1 if insert == "in-kernel" else 0)
     assert st["planes"] > 3000
 
 
@@ -120,4 +123,6 @@ def test_update_map_from_empty():
     """No prior map: the scan finds no residuals at first and only inserts (the map, roots included,
     is created by UpdateVoxelMap); later buckets of the same scan already match against it."""
     st = _stream_case(streaming=True, empty_map=True, stream0=900, n_scans=1)
+    assert st["nodes"] > 3000 and st["points"] > 20000
+    st = _stream_case(streaming=True, empty_map=True, stream0=900, n_scans=1, fused_insert=1)
     assert st["nodes"] > 3000 and st["points"] > 20000
