@@ -123,14 +123,17 @@ __device__ __noinline__ void fused_drain_queue(FusedSmem* sm, const FusedArgs& a
 template <bool INL> struct InlineSel { typedef FusedInline type; };
 template <> struct InlineSel<false> { typedef FusedNoInline type; };
 
-// A grid-wide barrier out of the flagged-row all-reduce (every block contributes a zero row): the block's earlier global
-// writes are fenced first, and what the other blocks wrote is read through L2 afterwards (ld.global.cg / TMA).
+// A grid-wide barrier out of the flagged-row all-reduce (every block contributes a zero row). Release side: every thread
+// fences its earlier global writes. Acquire side: a gpu-scope fence AFTER the barrier — on this architecture it also
+// invalidates the SM's L1 (CCTL.IVALL, see the SASS), so the plain (L1-cached) loads of the next phase cannot be served from
+// a line cached before another SM rewrote it; the read-only path (ld.global.nc) is not used on the map in these kernels.
 __device__ __forceinline__ void grid_sync(const FusedArgs& a, uint32_t& sync_idx) {
     __threadfence();
     __syncthreads();
     if (threadIdx.x < 32) (void)ll_allreduce(a.ll, sync_idx & 1u, a.epoch + sync_idx, blockIdx.x, gridDim.x, 0.0, (int)threadIdx.x);
     ++sync_idx;
     __syncthreads();
+    __threadfence();
 }
 
 // OBS: an inertial / kinematic queue is drained before every bucket. INL: the small inputs ride in the parameter block.
