@@ -98,7 +98,8 @@ struct lk_context {
     DevBuf small_in, small_out, fx, fP, fQ, fclk;
     PinnedBuf h_small_in, h_small_out;
     DevView chunks, stepinit, x_in, P_in, clk_in, Q, x, P, clk, n_eff;
-    size_t out_off_P = 0, out_off_clk = 0, out_off_neff = 0, out_bytes = 0;
+    size_t out_off_P = 0, out_off_clk = 0, out_off_neff = 0, out_off_status = 0, out_bytes = 0;
+    DevView status;
     DevBuf dbg_ok, dbg_h, dbg_z, dbg_R, dbg_key, tmp, trace, bar;
     DevBuf ins_pts, ins_root, ins_pend, ins_touched, ins_counters, ins_list;
     uint64_t ins_pend_nodes = 0;
@@ -665,11 +666,14 @@ static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P
     h->out_off_P = al((size_t)batch * sizeof(lk_state));
     h->out_off_clk = h->out_off_P + al((size_t)batch * 900 * 8);
     h->out_off_neff = h->out_off_clk + al((size_t)batch * sizeof(lk_stream_clock));
-    h->out_bytes = h->out_off_neff + al((size_t)batch * 4);
+    h->out_off_status = h->out_off_neff + al((size_t)batch * 4);
+    h->out_bytes = h->out_off_status + 256;
     LK_CUDA(h, h->small_out.ensure(h->out_bytes));
     LK_CUDA(h, h->h_small_out.ensure(h->out_bytes));
     char* dout = (char*)h->small_out.p;
     h->x.p = dout; h->P.p = dout + h->out_off_P; h->clk.p = dout + h->out_off_clk; h->n_eff.p = dout + h->out_off_neff;
+    h->status.p = dout + h->out_off_status;
+    std::memset((char*)h->h_small_out.p + h->out_off_status, 0, 4);
     cudaStream_t s = h->stream;
     if (want_direct && h->direct_io && batch == 1 && h->use_fused && h->lane_cache && h->max_chunk_pts <= 256 && total &&
         h->map.ready()) {
@@ -683,6 +687,7 @@ static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P
             h->direct_world = dw ? (float4*)dw : h->world.as<float4>();
             char* hout = (char*)h->h_small_out.p;  // page-locked: the kernel stores the filter straight into it
             h->x.p = hout; h->P.p = hout + h->out_off_P; h->clk.p = hout + h->out_off_clk; h->n_eff.p = hout + h->out_off_neff;
+            h->status.p = hout + h->out_off_status;
             if (h->inline_in && max_buckets <= (uint32_t)FUSED_INLINE_STEPS) {
                 if (h->Q_shadow.size() != 900 || std::memcmp(h->Q_shadow.data(), Q, 900 * 8) != 0) {
                     LK_CUDA(h, h->Qc.ensure(900 * 8));
@@ -854,6 +859,7 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         fa.P = h->P.as<double>();
         fa.clk = h->clk.as<lk_stream_clock>();
         fa.n_eff = h->n_eff.as<uint32_t>();
+        fa.status = h->status.as<uint32_t>();
         // tags of the flagged rows: one per (step, iteration); restart (with a cleared buffer) long before the 32-bit wrap
         const uint32_t need = h->n_steps * ((uint32_t)iters + 2u) + 1u;  // + two barriers per bucket with the insert inside
         if (h->ll_epoch > 0xE0000000u || need > 0x10000000u) {
@@ -1070,11 +1076,17 @@ int lk_batch_fetch(lk_handle h, lk_state* x_out, double* P_out, lk_stream_clock*
     }
     LK_CUDA(h, cudaStreamSynchronize(s));
     LK_CUDA(h, cudaGetLastError());
-    {
-        const int rc = check_stall(h);
-        if (rc) return rc;
-    }
     const char* ho = (const char*)h->h_small_out.p;
+    if (small && h->fused_launches_since_check) {
+        // the per-scan kernel leaves one status word with its outputs: only a non-zero one is worth the detailed read-back
+        uint32_t st;
+        std::memcpy(&st, ho + h->out_off_status, 4);
+        if (st) {
+            const int rc = check_stall(h);
+            if (rc) return rc;
+        }
+        h->fused_launches_since_check = 0;
+    }
     if (x_out) std::memcpy(x_out, ho, (size_t)batch * sizeof(lk_state));
     if (P_out) std::memcpy(P_out, ho + h->out_off_P, (size_t)batch * 900 * 8);
     if (clk_out) std::memcpy(clk_out, ho + h->out_off_clk, (size_t)batch * sizeof(lk_stream_clock));

@@ -304,7 +304,12 @@ __global__ void __launch_bounds__(BLOCK, 1) k_scan_fused(const __grid_constant__
         for (int e = tid; e < 900; e += BLOCK) a.P[(size_t)scan * 900 + e] = sm->f.P[e];
         if (tid < 36) a.x[(size_t)scan * 36 + tid] = sm->f.x[tid];
         if (tid < 2) reinterpret_cast<double*>(a.clk + scan)[tid] = sm->clk[tid];
-        if (tid == 0) a.n_eff[scan] = n_eff_total;
+        if (tid == 0) {
+            a.n_eff[scan] = n_eff_total;
+            // did any wait of this launch give up (lk_llsync.cuh / lk_async.cuh watchdogs)? The host looks at this word first
+            // and only then pays for the detailed read-back
+            *a.status = (*reinterpret_cast<volatile uint32_t*>(a.ll.stall) ? 1u : 0u) | (*reinterpret_cast<volatile uint32_t*>(&lk_stall_note[0]) ? 2u : 0u);
+        }
     }
     FT(31);
 }

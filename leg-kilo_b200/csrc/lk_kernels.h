@@ -122,6 +122,7 @@ struct FusedArgs {
     double* P;
     lk_stream_clock* clk;
     uint32_t* n_eff;
+    uint32_t* status;  // one word next to the outputs: non-zero when a device-side wait of this launch gave up
     LLView ll;       // flagged rows of the barrier-free all-reduce (lk_llsync.cuh)
     uint32_t epoch;  // tag of this launch's first exchange; the launch uses epoch .. epoch + n_steps * (iters + 2) - 1
     int iters;
