@@ -2,8 +2,9 @@
 
 ctypes wrapper over oracle/liblko.so, the CPU restatement of the reference hot path. Only tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this; the
-product (leg-kilo_b200/) never does. PARITY UNPINNED by the reference (it ships no golden
-vectors and cannot be compiled here) — see oracle/README.md for the self-made pins.
+product (leg-kilo_b200/) never does. The reference ships no golden vectors; the restatement is pinned against the
+reference's OWN sources compiled here over stand-in third-party headers (oracle/lkref.py, oracle/ref/,
+tests/test_oracle_vs_reference.py) — see oracle/README.md for what that does and does not cover.
 """
 from __future__ import annotations
 

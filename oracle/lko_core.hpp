@@ -3,10 +3,11 @@
 // CPU restatement of Leg-KILO's per-scan ESKF LiDAR point-to-plane measurement update, written
 // from the reference's behaviour (not copied): every function cites the reference lines it
 // follows. Float temporaries, thresholds and quirks of the reference are reproduced on purpose
-// (SURVEY.md §8a). PARITY UNPINNED BY THE REFERENCE: the reference ships no tests, golden
-// vectors or fixtures and cannot be compiled here (no Eigen/PCL/ROS); pins are self-made:
-// literal-vs-information gain, the independent numpy mirror in tests/, analytic cases, and
-// oracle/_ref (reference translation units compiled against oracle/shim stand-in headers).
+// (SURVEY.md §8a). The reference ships no tests, golden vectors or fixtures; this restatement is
+// pinned against oracle/_ref — the reference's own eskf.cc / voxel_map.cc / KILO.cc compiled from
+// /root/reference over the stand-in third-party headers of oracle/ref/shim
+// (tests/test_oracle_vs_reference.py) — and by the literal-vs-information gain check, the
+// independent numpy mirror in tests/, analytic cases and property tests (oracle/README.md).
 #pragma once
 #include <array>
 #include <cstdint>

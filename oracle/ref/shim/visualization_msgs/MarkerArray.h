@@ -1,0 +1,6 @@
+#pragma once
+#include <vector>
+#include <visualization_msgs/Marker.h>
+namespace visualization_msgs {
+struct MarkerArray { std::vector<Marker> markers; };
+}

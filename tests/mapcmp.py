@@ -66,3 +66,55 @@ def compare_blobs(blob_a, blob_b, rtol=1e-6, check_points=True, pt_atol=1e-12, v
     for key in sorted(ka):
         cmp_node(ka[key], kb[key], (key,))
     return stats
+
+
+DIGEST_DTYPE = np.dtype([("flags", "u4"), ("pts_count", "i4"), ("new_points", "i4"), ("key", "i4", (3,)), ("center", "f8", (3,)),
+                         ("normal", "f8", (3,)), ("d", "f8"), ("radius", "f8"), ("var_nn", "f8"), ("var_cc", "f8")])
+
+
+def digest(blob):
+    """A compact, order-canonical summary of a map blob for committed fixtures: one record per octree node in depth-first
+    order (roots by ascending key, children by octant), sign-canonical plane, and the traces of the two diagonal blocks
+    of plane_var (both invariant under the normal's sign)."""
+    _, roots, nodes, aux, _ = abi.parse_map_blob(blob)
+    out = []
+
+    def walk(i, key):
+        A, X = nodes[i], aux[i]
+        f = int(A["flags"])
+        rec = np.zeros(1, DIGEST_DTYPE)
+        rec["flags"] = f & 0x00ffff07
+        rec["key"] = key
+        interior = bool(f & 2) and not (f & 1) and ((f >> 16) & 0xff)
+        if not interior:
+            rec["pts_count"] = X["pts_count"]; rec["new_points"] = X["new_points"]
+        if f & 1:
+            n, d, pv = _canon_plane(A)
+            rec["center"] = A["center"]; rec["normal"] = n; rec["d"] = d; rec["radius"] = A["radius"]
+            rec["var_nn"] = np.trace(pv[:3, :3]); rec["var_cc"] = np.trace(pv[3:, 3:])
+        out.append(rec)
+        for c in range(8):
+            if (f >> 16) & (1 << c):
+                walk(int(A["child_base"]) + c, key)
+
+    for r in sorted(roots, key=lambda r: tuple(r["key"])):
+        walk(int(r["node"]), r["key"])
+    return np.concatenate(out) if out else np.zeros(0, DIGEST_DTYPE)
+
+
+def compare_digest(dig_ref, blob, rtol=1e-6, center_atol=1e-10):
+    """dig_ref: digest() of the reference's map (a committed fixture); blob: the map under test."""
+    dg = digest(blob)
+    assert len(dg) == len(dig_ref), (len(dg), len(dig_ref))
+    np.testing.assert_array_equal(dg["key"], dig_ref["key"])
+    np.testing.assert_array_equal(dg["flags"], dig_ref["flags"])
+    np.testing.assert_array_equal(dg["pts_count"], dig_ref["pts_count"])
+    np.testing.assert_array_equal(dg["new_points"], dig_ref["new_points"])
+    pl = (dig_ref["flags"] & 1).astype(bool)
+    np.testing.assert_allclose(dg["center"][pl], dig_ref["center"][pl], rtol=0, atol=center_atol)
+    np.testing.assert_allclose(dg["normal"][pl], dig_ref["normal"][pl], rtol=0, atol=rtol)
+    np.testing.assert_allclose(dg["d"][pl], dig_ref["d"][pl], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(dg["radius"][pl], dig_ref["radius"][pl], rtol=1e-6)
+    np.testing.assert_allclose(dg["var_nn"][pl], dig_ref["var_nn"][pl], rtol=rtol)
+    np.testing.assert_allclose(dg["var_cc"][pl], dig_ref["var_cc"][pl], rtol=rtol)
+    return dict(nodes=len(dg), planes=int(pl.sum()))

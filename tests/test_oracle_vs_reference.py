@@ -1,0 +1,269 @@
+"""Pins the CPU oracle (oracle/lko_core.cpp, a restatement) against the REFERENCE ITSELF run here: oracle/_ref/liblkref.so
+is the reference's own eskf.cc / voxel_map.cc / KILO.cc compiled unmodified from /root/reference (oracle/ref/Makefile)
+over stand-in third-party headers (oracle/ref/shim/: Eigen, PCL, ROS messages, glog, yaml-cpp are not in this image).
+
+Same buffers into both; compared: calcBodyCov, init_plane, BuildVoxelMap (whole map, node by node), predictUpdatePoint
+(state, covariance, clocks, world cloud, success count, map after UpdateVoxelMap), the one- and zero-residual branches,
+predictUpdateImu / predictUpdateKinImu, the first frame of KILO::process (StateInitial + BuildVoxelMap) and later frames
+(sort, bucket loop, queue drain). Tolerances are floating-point summation order only: the stand-in linear algebra and
+the oracle's add in different orders, and eigenvector signs are free in both (mapcmp canonicalises them).
+
+Skipped where neither the built library nor /root/reference exists; tests/golden/ref_*.npz (made by
+tests/golden/make_ref_golden.py from the same library) carry the pin to such boxes."""
+import numpy as np
+import pytest
+
+import lko
+import lkref
+import mapcmp
+from legkilo_b200 import abi, synth
+
+pytestmark = pytest.mark.skipif(not lkref.available(), reason="needs oracle/_ref/liblkref.so or /root/reference")
+
+TOL = 1e-10
+
+
+def _rel_state(xa, xb, x0):
+    return np.abs(lko.boxminus(xa, xb)).max() / max(np.abs(lko.boxminus(xb, x0)).max(), 1e-12)
+
+
+def _rel_cov(Pa, Pb):
+    return np.abs(np.asarray(Pa) - np.asarray(Pb)).max() / np.abs(Pb).max()
+
+
+def _scene(cfg_name, half=8.0, wall=6.25, stream=8200, streaming=False, n_rings=16, n_az=120):
+    cfg = abi.CONFIGS[cfg_name]
+    R, t = abi.extrinsics(cfg)
+    sc = synth.BoxScene(ground_half_extent=half, wall=wall)
+    pw, pb = sc.map_points(ext_R=R, ext_t=t)
+    rv, tv = synth.random_poses(1, 2e-3, 0.02, stream=stream)
+    scan = sc.scan(rotvec=rv[0], trans=tv[0], ext_R=R, ext_t=t, blind=cfg["blind"], stream=stream + 1, n_rings=n_rings,
+                   n_az=n_az, fov_deg=(-15.0, 15.0), streaming=streaming)
+    return cfg, pw, pb, scan
+
+
+def _moving_state():
+    x0 = abi.default_states(1)
+    x0["vel"][0] = (0.4, -0.2, 0.05)
+    x0["imu_w"][0] = (0.02, -0.03, 0.15)
+    x0["imu_a"][0] = (0.3, 0.1, 9.7)
+    x0["ba"][0] = (0.01, -0.02, 0.03)
+    x0["bw"][0] = (1e-3, 2e-3, -1e-3)
+    return x0
+
+
+def _pair(cfg, pw, pb, x0, clk, imu_mode_only=True, acc_norm=9.79, **map_kw):
+    o = lko.Oracle(cfg)
+    r = lkref.Reference(cfg, imu_mode_only=imu_mode_only, gravity=9.81, acc_norm=acc_norm)
+    o.set_options(gain_mode=lko.GAIN_LITERAL, iters=1, update_map=True, imu_mode_only=imu_mode_only, gravity=9.81, acc_norm=acc_norm)
+    o.build_voxel_map(pw, pb, **map_kw)
+    r.build_voxel_map(pw, pb, **map_kw)
+    P0, Q = abi.init_cov(1), abi.process_cov_Q(cfg)
+    for obj in (o, r):
+        obj.set_filter(x0, P0, Q, clk)
+    return o, r
+
+
+def _same_filter(o, r, x0, tol=TOL):
+    xo, Po, _, co = o.get_filter()
+    xr, Pr, _, cr = r.get_filter()
+    assert _rel_state(xo, xr, x0) < tol, _rel_state(xo, xr, x0)
+    assert _rel_cov(Po, Pr) < tol, _rel_cov(Po, Pr)
+    assert co.tobytes() == cr.tobytes()
+
+
+def test_process_covariance_q_matches_init_process_cov():
+    for name in ("leg_fusion", "hilti"):
+        cfg = abi.CONFIGS[name]
+        r = lkref.Reference(cfg)
+        r.init_process_cov()  # ESKF::initProcessCovQ (eskf.cc:47-62)
+        assert r.get_filter()[2].tobytes() == abi.process_cov_Q(cfg).ravel().tobytes()
+
+
+def test_calc_body_cov_matches():
+    g = np.random.default_rng(5)
+    pts = g.uniform(-30, 30, (64, 3))
+    pts[:4, 2] = 0.0  # the pb[2] == 0 -> 1e-4 patch (voxel_map.cc:23)
+    for p in pts:
+        co, po = lko.calc_body_cov(p, 0.02, 0.05)
+        cr, pr = lkref.calc_body_cov(p, 0.02, 0.05)
+        assert po.tobytes() == pr.tobytes()
+        np.testing.assert_allclose(co, cr, rtol=0, atol=1e-13 * np.abs(cr).max())
+
+
+@pytest.mark.parametrize("kind", ["plane", "blob", "edge"])
+def test_init_plane_matches(kind):
+    g = np.random.default_rng({"plane": 1, "blob": 2, "edge": 3}[kind])
+    for trial in range(20):
+        n = int(g.integers(6, 60))
+        if kind == "plane":
+            nrm = g.standard_normal(3); nrm /= np.linalg.norm(nrm)
+            u = np.cross(nrm, [1.0, 0.3, -0.2]); u /= np.linalg.norm(u); v = np.cross(nrm, u)
+            pw = g.uniform(-0.25, 0.25, (n, 1)) * u + g.uniform(-0.25, 0.25, (n, 1)) * v + 0.005 * g.standard_normal((n, 1)) * nrm
+        elif kind == "blob":
+            pw = g.uniform(-0.25, 0.25, (n, 3))
+        else:  # two planes meeting: smallest eigenvalue near the threshold
+            pw = g.uniform(-0.25, 0.25, (n, 3)); pw[: n // 2, 2] = 0.0; pw[n // 2:, 0] = 0.2 * g.uniform(0, 1)
+        pw = pw + g.uniform(-20, 20, 3)
+        A = 0.01 * g.standard_normal((n, 3, 3))
+        var = A @ A.transpose(0, 2, 1) + 1e-5 * np.eye(3)
+        po = lko.init_plane(pw, var.reshape(n, 9))
+        pr = lkref.init_plane(pw, var.reshape(n, 9))
+        assert po["is_plane"] == pr["is_plane"]
+        if not pr["is_plane"]:
+            continue
+        s = 1.0 if np.dot(po["normal"], pr["normal"]) > 0 else -1.0
+        np.testing.assert_allclose(po["center"], pr["center"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(s * po["normal"], pr["normal"], rtol=0, atol=1e-9)
+        assert abs(s * po["d"] - pr["d"]) <= 2e-6 * max(1.0, abs(pr["d"]))  # d_ is a float
+        assert abs(po["radius"] - pr["radius"]) <= 1e-6 * pr["radius"]
+        np.testing.assert_allclose(po["eig"], pr["eig"], rtol=1e-5, atol=1e-9)
+        pvo = po["plane_var"].copy(); pvo[:3, 3:] *= s; pvo[3:, :3] *= s
+        assert np.abs(pvo - pr["plane_var"]).max() / np.abs(pr["plane_var"]).max() < 1e-7
+
+
+@pytest.mark.parametrize("cfg_name,rot", [("leg_fusion", False), ("hilti", False), ("leg_fusion", True)])
+def test_build_voxel_map_matches(cfg_name, rot):
+    cfg, pw, pb, _ = _scene(cfg_name)
+    kw = {}
+    if rot:  # a first frame seen from a rotated pose: BuildVoxelMap's (rot * extR) term (voxel_map.cc:305-307)
+        G = synth.exp_so3([0.02, -0.01, 0.7])
+        R, t = abi.extrinsics(cfg)
+        pw = ((pb.astype(np.float64) @ R.T + t) @ G.T + [1.5, -2.0, 0.1]).astype(np.float32)
+        kw = dict(R=G, rot_cov=2e-6 * np.eye(3), pos_cov=3e-6 * np.eye(3))
+    o = lko.Oracle(cfg); r = lkref.Reference(cfg)
+    o.build_voxel_map(pw, pb, **kw); r.build_voxel_map(pw, pb, **kw)
+    assert o.num_roots() == r.num_roots() > 100
+    st = mapcmp.compare_blobs(r.map_export(), o.map_export(), rtol=1e-7, pt_atol=0.0, var_rtol=1e-12)
+    assert st["planes"] > 100 and st["points"] > 1000
+
+
+@pytest.mark.parametrize("cfg_name", ["leg_fusion", "hilti"])
+def test_predict_update_point_matches(cfg_name):
+    """Three consecutive buckets through KILO::predictUpdatePoint (KILO.cc:108-233): predict, residuals with the
+    neighbour-voxel retry, the literal n x n gain (eskf.cc:100-107), re-projection and UpdateVoxelMap."""
+    cfg, pw, pb, scan = _scene(cfg_name)
+    x0 = _moving_state()
+    clk = np.zeros(1, abi.CLOCK_DTYPE); clk["last_predict_time"] = 99.99; clk["last_update_time"] = 99.985
+    o, r = _pair(cfg, pw, pb, x0, clk)
+    t = 100.0
+    for k in range(3):
+        pts = scan[k * 300:(k + 1) * 300]
+        ro = o.predict_update_point(t, pts)
+        rr = r.predict_update_point(t, pts)
+        assert ro["n_eff"] == rr["n_eff"] > 200 and ro["updated"] == rr["updated"]
+        np.testing.assert_allclose(ro["world"], rr["world"], rtol=0, atol=2e-6)  # float32 cloud: one ulp at 10 m
+        assert (ro["world"][:, 3] == rr["world"][:, 3]).all()
+        _same_filter(o, r, x0)
+        t += 0.002
+    st = mapcmp.compare_blobs(r.map_export(), o.map_export(), rtol=1e-6, pt_atol=1e-11, var_rtol=1e-8)
+    assert st["planes"] > 100
+
+
+def test_single_and_zero_residual_branches_match():
+    """dof_measurements == 1 takes the scalar branch (eskf.cc:92-99); no residual leaves the filter alone but still
+    inserts the bucket (KILO.cc:187, :232)."""
+    cfg, pw, pb, scan = _scene("leg_fusion")
+    x0 = _moving_state()
+    clk = np.zeros(1, abi.CLOCK_DTYPE); clk["last_predict_time"] = 9.99; clk["last_update_time"] = 9.99
+    o, r = _pair(cfg, pw, pb, x0, clk)
+    far = scan[:8].copy(); far[:, :3] += (300.0, 300.0, 50.0)  # nowhere near the map
+    for pts, want in ((scan[:1], 1), (far, 0), (np.concatenate([far, scan[5:6]]), 1)):
+        ro = o.predict_update_point(10.0, pts); rr = r.predict_update_point(10.0, pts)
+        assert ro["n_eff"] == rr["n_eff"] == want and ro["updated"] == rr["updated"] == bool(want)
+        assert (ro["world"][:, 3] == rr["world"][:, 3]).all()
+        _same_filter(o, r, x0)
+    mapcmp.compare_blobs(r.map_export(), o.map_export(), rtol=1e-6, pt_atol=1e-11, var_rtol=1e-8)
+
+
+@pytest.mark.parametrize("kind", ["imu", "kin"])
+def test_inertial_and_kinematic_updates_match(kind):
+    cfg, pw, pb, _ = _scene("leg_fusion", half=2.0)
+    x0 = _moving_state()
+    clk = np.zeros(1, abi.CLOCK_DTYPE); clk["last_predict_time"] = 3.0; clk["last_update_time"] = 2.995
+    o, r = _pair(cfg, pw, pb, x0, clk, imu_mode_only=(kind == "imu"))
+    meas = synth.imu_stream(3.0, 3.05) if kind == "imu" else synth.kinimu_stream(3.0, 3.05)
+    for obj in (o, r):
+        (obj.obs_imu if kind == "imu" else obj.obs_kinimu)(meas)
+    _same_filter(o, r, x0, tol=1e-9)
+
+
+def _first_frame_numpy(meas, gravity):
+    """StateInitialByImu / ByKinImu::processing (state_initial.hpp:36-67, :74-105) restated with numpy."""
+    acc, gyr = meas["acc"], meas["gyr"]
+    mean_a, mean_w, n = acc[0].copy(), gyr[0].copy(), 1
+    for a, w in zip(acc, gyr):
+        mean_a += (a - mean_a) / n
+        mean_w += (w - mean_w) / n
+        n += 1
+    acc_norm = np.linalg.norm(mean_a)
+    return -mean_a / acc_norm * gravity, mean_w, acc_norm
+
+
+@pytest.mark.parametrize("kind", ["imu", "kin"])
+def test_process_first_frame_then_streaming_frames_match(kind):
+    """KILO::process end to end (KILO.cc:316-399). Frame 0 initialises gravity / gyro bias / covariance / Q and builds
+    the map from the raw cloud; frames 1-2 sort by curvature and walk the buckets, draining the inertial queue first.
+    std::sort is not stable, so the oracle is fed the cloud in the order the reference's sort left it in."""
+    cfg, _, pb, _ = _scene("leg_fusion", half=8.0)
+    R, t = abi.extrinsics(cfg)
+    sc = synth.BoxScene(ground_half_extent=8.0, wall=6.25)
+    r = lkref.Reference(cfg, imu_mode_only=(kind == "imu"), gravity=9.81, initialised=False)
+    mk = synth.imu_stream if kind == "imu" else synth.kinimu_stream
+    raw = np.concatenate([pb, np.zeros((len(pb), 1), np.float32)], axis=1)
+    m0 = mk(49.9, 50.0)
+    out = r.process(49.9, 50.0, raw, **{kind: m0})
+    assert out["ok"]
+    grav, bw, acc_norm = _first_frame_numpy(m0, 9.81)
+    assert abs(r.acc_norm() - acc_norm) < 1e-12
+    xr, Pr, Qr, cr = r.get_filter()
+    np.testing.assert_allclose(xr["grav"][0], grav, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(xr["bw"][0], bw, rtol=0, atol=1e-14)
+    assert Pr.tobytes() == abi.init_cov(1).ravel().tobytes() and Qr.tobytes() == abi.process_cov_Q(cfg).ravel().tobytes()
+    assert float(cr["last_predict_time"][0]) == float(cr["last_update_time"][0]) == 50.0
+    # the oracle starts from the reference's own first-frame filter; its map from the same float32 world cloud
+    # (KILO::pointLidarToWorld, KILO.cc:96-106: identity attitude, zero position)
+    pw = (pb.astype(np.float64) @ R.T + t).astype(np.float32)
+    np.testing.assert_array_equal(out["world"][:, :3], pw)
+    o = lko.Oracle(cfg)
+    o.set_options(gain_mode=lko.GAIN_LITERAL, iters=1, update_map=True, imu_mode_only=(kind == "imu"), gravity=9.81, acc_norm=r.acc_norm())
+    o.build_voxel_map(pw, pb, R=np.eye(3), rot_cov=Pr.reshape(30, 30)[:3, :3], pos_cov=Pr.reshape(30, 30)[3:6, 3:6])
+    o.set_filter(xr, Pr, Qr, cr)
+    mapcmp.compare_blobs(r.map_export(), o.map_export(), rtol=1e-7, pt_atol=0.0, var_rtol=1e-12)
+    x_init = xr.copy()
+    t0 = 50.0
+    for f in range(2):
+        rv, tv = synth.random_poses(1, 2e-3, 0.02, stream=8300 + f)
+        scan = sc.scan(rotvec=rv[0], trans=tv[0], ext_R=R, ext_t=t, blind=cfg["blind"], stream=8310 + f, n_rings=16, n_az=120,
+                       fov_deg=(-15.0, 15.0), streaming=True)
+        meas = mk(t0 + 0.001, t0 + 0.13, stream=60 + f)
+        out = r.process(t0, t0 + 0.1, scan, **{kind: meas})
+        assert out["ok"] and out["n_eff"] > 0.7 * len(scan)
+        assert np.array_equal(np.sort(out["body"][:, 3]), out["body"][:, 3])  # sorted by curvature
+        ro = o.process_scan(t0, out["body"], **{kind: meas})
+        assert ro["n_eff"] == out["n_eff"]
+        np.testing.assert_allclose(ro["world"], out["world"], rtol=0, atol=2e-6)
+        assert (ro["world"][:, 3] == out["world"][:, 3]).all()
+        _same_filter(o, r, x_init, tol=1e-8)
+        t0 += 0.1
+    st = mapcmp.compare_blobs(r.map_export(), o.map_export(), rtol=1e-5, pt_atol=1e-10, var_rtol=1e-7)
+    assert st["planes"] > 100
+
+
+def test_map_sliding_rule_matches():
+    """VoxelMapManager::mapSliding / clearMemOutOfMap (voxel_map.cc:552-596): the numpy rule that
+    tests/test_facade_compiles.py holds lk_map_slide to, checked against the reference on the same sequence."""
+    cfg = dict(abi.CONFIGS["leg_fusion"], half_map_size=10, sliding_thresh=8.0)
+    _, pw, pb, _ = _scene("leg_fusion")
+    r = lkref.Reference(cfg)
+    r.build_voxel_map(pw, pb)
+    keys0 = abi.parse_map_blob(r.map_export())[1]["key"]
+    assert not r.map_slide([3.0, 0.0, 0.0])  # closer than sliding_thresh to the last slide position (the origin)
+    assert r.num_roots() == len(keys0)
+    assert r.map_slide([9.0, 1.0, 0.2])
+    k = np.floor(np.array([9.0, 1.0, 0.2]) / 0.5).astype(int)
+    keep = np.all((keys0 <= k + 10) & (keys0 >= k - 10), axis=1)
+    assert 0 < keep.sum() < len(keys0)
+    keys1 = abi.parse_map_blob(r.map_export())[1]["key"]
+    assert {tuple(x) for x in keys1.tolist()} == {tuple(x) for x in keys0[keep].tolist()}
+    assert not r.map_slide([9.5, 1.0, 0.2])  # measured from the position of the last slide now
