@@ -110,8 +110,9 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []  # (arrival time, csv line)
         self.proc = None
+        self.t_begin = None
 
     def start(self):
         try:
@@ -125,11 +126,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        """The timed region starts now (the sampler itself is started before the warm-up: nvidia-smi needs a few hundred
+        milliseconds to come up, longer than a 20-step timed region lasts)."""
+        self.t_begin = time.time()
 
     def stop(self):
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        t_end = time.time()
         time.sleep(0.05)
         self.proc.terminate()
         try:
@@ -138,7 +145,16 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        # a sample reports the 20 ms before it arrived: keep those that overlap the timed region; when the region is
+        # shorter than the sampling period and none does, the last ones before its end (the device has been under the
+        # same load since the warm-up began)
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        rows = [r for (t, r) in self.rows if t0 <= t <= t_end + 0.06]
+        window = "timed region"
+        if not rows:
+            rows = [r for (t, r) in self.rows if t <= t_end + 0.06][-3:]
+            window = "last samples of the warm-up (timed region shorter than the 20 ms sampling period)"
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 6:
                 continue
@@ -152,7 +168,7 @@ class ClockSampler:
         # "under load" = samples above the idle clock (the sampler also sees the gaps around the timed region)
         load = [v for v in sm if v > 500.0] or sm
         return dict(sm_mhz=float(np.median(load)) if load else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm), samples_under_load=len(load))
+                    reasons=sorted(reasons), samples=len(sm), samples_under_load=len(load), window=window)
 
 
 def build_workload(w, rank, ring):
@@ -501,6 +517,8 @@ def main():
     if w["batch"] == 1 and not args.no_throughput:
         tmode = throughput_mode(args, rank, world, local_rank, dist, hbm_peak)
 
+    sampler = ClockSampler(local_rank)  # started well ahead: nvidia-smi takes a few hundred ms to deliver its first row
+    sampler.start()
     t_setup = time.time()
     wl = build_workload(w, rank, ring)
     wl["rank"] = rank
@@ -537,8 +555,7 @@ def main():
         eng.run_range((i % groups) * B, B, iters=w["iters"])
     eng.sync()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark_begin()
     eng.timer_start()
     work = 0
     for i in range(K):

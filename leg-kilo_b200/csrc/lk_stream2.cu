@@ -35,6 +35,10 @@ struct S2Smem {
     static constexpr int FB_CAP = ((S2_MAXPTS / 32 + S2_WARPS - 1) / S2_WARPS) * 32;
     __align__(16) unsigned char st[S2_WARPS][2][S2_STAGE_BYTES];
     double slice[S2_WARPS * 32];
+    // A = sum h^T h / R (21 terms) of every thread, [term][thread]: at 168 registers the compiler kept these in local memory,
+    // whose footprint (two blocks x 192 threads) does not fit the 28 KB of L1 left beside the stages — every reload was an L2
+    // round trip (local-load hit rate 1 % in ncu). Conflict-free 8-byte accesses, no synchronisation: a thread owns its column.
+    double accA[21][S2_WARPS * 32];
     uint16_t fb[S2_WARPS][FB_CAP];  // chunk-relative point indices
     uint32_t nfb[S2_WARPS];
     ScanConst sc;
@@ -102,6 +106,25 @@ __device__ __forceinline__ bool eval_plane_hot(const unsigned char* slot, const 
     return true;
 }
 
+// accumulate_row (lk_pass.cuh) with the 21 terms of A in shared memory: same products, same order, same contraction.
+template <int NT>
+__device__ __forceinline__ void accumulate_row_sm(const Row& row, double* colA, double (&rest)[8]) {
+    const double w = 1.0 / row.R;
+    int q = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const double hw = row.h[r] * w;
+#pragma unroll
+        for (int c = r; c < 6; ++c) {
+            colA[q * NT] += hw * row.h[c];
+            ++q;
+        }
+        rest[r] += hw * row.z;
+    }
+    rest[6] += row.R;
+    rest[7] += 1.0;
+}
+
 template <int S2_THREADS>
 __global__ void __launch_bounds__(S2_THREADS, 2) k_residual_stream2(const __grid_constant__ ResidualArgs a) {
     constexpr int S2_WARPS = S2_THREADS / 32;
@@ -126,9 +149,12 @@ __global__ void __launch_bounds__(S2_THREADS, 2) k_residual_stream2(const __grid
     const int thr = third < 3 ? 0 : 0x7fffffff;
     const int thr_last = third < 2 ? 0 : 0x7fffffff;  // the 11th instruction carries lanes 30, 31 only
 
-    double acc[32];
+    double* colA = &sm->accA[0][tid];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+    for (int i = 0; i < 21; ++i) colA[i * S2_THREADS] = 0.0;
+    double rest[8];  // b (6) | sum R | count
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rest[i] = 0.0;
     uint32_t nfbw = 0;
 
     // group i of this warp starts at point (warp + i * S2_WARPS) * 32
@@ -195,7 +221,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2) k_residual_stream2(const __grid
                 float lx, ly, lz;
                 prepare_point(pt, sc, g, pc, lx, ly, lz);
                 Row row;
-                if (eval_plane_hot(slot, pc, sc, g, row)) accumulate_row(row, acc);
+                if (eval_plane_hot(slot, pc, sc, g, row)) accumulate_row_sm<S2_THREADS>(row, colA, rest);
                 else fail = true;  // not a plane here, or gated out: finished below with the full reference sequence
             }
             const uint32_t m = __ballot_sync(0xffffffffu, fail);
@@ -207,6 +233,17 @@ __global__ void __launch_bounds__(S2_THREADS, 2) k_residual_stream2(const __grid
     }
     cp_async_wait_group<0>();
     if (lane == 0) sm->nfb[warp] = nfbw;
+    // the rare rows below and the reduction work on a register image (layout of lk_kernels.h: A | b | sum R | count)
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) acc[i] = colA[i * S2_THREADS];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) acc[ACC_B + i] = rest[i];
+    acc[ACC_SUMR] = rest[6];
+    acc[ACC_CNT] = rest[7];
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+        if (i != ACC_SUMR && i != ACC_CNT && !(i < 21) && !(i >= ACC_B && i < ACC_B + 6)) acc[i] = 0.0;
     __syncthreads();
     {
         uint32_t cnt[S2_WARPS], total = 0;

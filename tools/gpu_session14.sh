@@ -1,15 +1,14 @@
 #!/bin/bash
+# stream2 accumulators in shared memory: parity + throughput numbers + default line (clock sampler check)
 cd "$(dirname "$0")/.." && mkdir -p gpurun_out
-timeout -k 5 300 python -m pytest tests/test_gpu_map.py tests/test_gpu_filter.py tests/test_gpu_parity.py tests/test_facade_compiles.py tests/test_gpu_edges.py -m gpu -x -q > gpurun_out/s14_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s14_pytest.log
-tail -12 gpurun_out/s14_pytest.log
-for wl in nclt_stream leg_fusion_stream; do
-timeout -k 5 120 python bench.py --workload $wl --steps 40 --warmup 5 > gpurun_out/s14_$wl.json 2> gpurun_out/s14_err.log
-python - <<PY
-import json
-try:
-    d=json.load(open("gpurun_out/s14_$wl.json"))
-    print("$wl p50 %.3f ms mean %.3f p95 %.3f" % (d["value"], d["ms_per_step"], d["p95_ms"]), d["config"]["n_eff_mean"])
-except Exception as e: print("$wl failed", e)
+( timeout -k 10 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_inputs.py tests/test_properties.py tests/test_reference_golden.py -m gpu -x -q ) 2>&1 | tail -4
+run() { name=$1; shift; timeout -k 10 600 python bench.py "$@" > gpurun_out/s14_$name.json 2> gpurun_out/s14_$name.err || echo "$name FAILED"; tail -c 300 gpurun_out/s14_$name.err; }
+run diter_b128 --workload diter_b128 --steps 6 --warmup 3 --no-cpu-baseline --no-e2e
+run synth100k_b1024 --workload synth100k_b1024 --steps 6 --warmup 3 --no-cpu-baseline --no-e2e
+run default --gpus 1 --steps 20 --warmup 5
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/s14_*.json")):
+    d = json.load(open(f)); r = d.get("roofline") or {}
+    print(f.split("s14_")[1][:-5], "value %.4e ms/step %.4f frac %s" % (d["value"], d["ms_per_step"], r.get("frac")), d.get("clocks"), (r.get("throughput_mode") or {}).get("frac"))
 PY
-tail -2 gpurun_out/s14_err.log
-done
