@@ -1,15 +1,5 @@
 #!/bin/bash
+# re-capture the throughput kernel after the shared-memory accumulators (ncu --set full on the configs[3] shard)
 cd "$(dirname "$0")/.." && mkdir -p gpurun_out
-timeout -k 5 200 python -m pytest tests/test_gpu_map.py tests/test_gpu_filter.py -m gpu -x -q > gpurun_out/s15_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s15_pytest.log
-tail -4 gpurun_out/s15_pytest.log
-for wl in nclt_stream leg_fusion_stream; do
-timeout -k 5 120 python bench.py --workload $wl --steps 40 --warmup 5 > gpurun_out/s15_$wl.json 2> gpurun_out/s15_err.log
-python - <<PY
-import json
-try:
-    d=json.load(open("gpurun_out/s15_$wl.json"))
-    print("$wl p50 %.3f ms mean %.3f p95 %.3f" % (d["value"], d["ms_per_step"], d["p95_ms"]), d["config"]["n_eff_mean"])
-except Exception as e: print("$wl failed", e)
-PY
-tail -2 gpurun_out/s15_err.log
-done
+timeout -k 10 700 ncu --set full --clock-control none --import-source on -k regex:k_residual_stream2 -s 6 -c 1 -f -o gpurun_out/r2_stream2 python bench.py --workload synth100k_b1024 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu3.log 2>&1; tail -2 gpurun_out/ncu3.log | cut -c1-200
+ls -la gpurun_out/r2_stream2.ncu-rep
