@@ -958,16 +958,10 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
     for (uint32_t k = 0; k < h->n_steps; ++k) {
         const StepInit* hin = tin.data() + (size_t)k * batch;
         uint32_t c0 = hin[first].chunk_begin, c1 = hin[first + count - 1].chunk_end;
-        if (mq && hin[first].active) {  // samples with stamp < bucket time (KILO.cc:379-390)
-            uint32_t m1 = mi;
-            while (m1 < mq->n && mq->stamps[m1] < hin[first].t_bucket) ++m1;
-            if (m1 > mi) {
-                launch_filter_obs(h->x.as<double>() + (size_t)first * 36, h->P.as<double>() + (size_t)first * 900, h->Q.as<double>(),
-                                  h->clk.as<lk_stream_clock>() + first, mq->d_imu ? mq->d_imu + mi : nullptr,
-                                  mq->d_kin ? mq->d_kin + mi : nullptr, m1 - mi, h->ec, mq->gravity, mq->acc_norm, s);
-                ++h->acc_launches;
-                mi = m1;
-            }
+        uint32_t m_obs0 = mi, m_obs1 = mi;  // samples with stamp < bucket time (KILO.cc:379-390)
+        if (mq && hin[first].active) {
+            while (m_obs1 < mq->n && mq->stamps[m_obs1] < hin[first].t_bucket) ++m_obs1;
+            mi = m_obs1;
         }
         PredictArgs pa;
         pa.init = d_inits + (size_t)k * batch;
@@ -985,7 +979,11 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
         pa.reset = (k == 0 && !mq) ? 1 : 0;
         pa.scan_first = (int)first;
         pa.batch = (int)count;
-        launch_predict_prepare(pa, s);
+        if (mq && count == 1 && hin[first].active)  // the queue drain and the bucket's predict share one launch and one copy of the filter
+            launch_obs_predict_prepare(pa, mq->d_imu ? mq->d_imu + m_obs0 : nullptr, mq->d_kin ? mq->d_kin + m_obs0 : nullptr,
+                                       m_obs1 - m_obs0, h->ec, mq->gravity, mq->acc_norm, s);
+        else
+            launch_predict_prepare(pa, s);
         ++h->acc_launches;
         for (int it = 0; it < iters; ++it) {
             ResidualArgs ra = residual_args(h, d_chunks);

@@ -129,6 +129,54 @@ __global__ void __launch_bounds__(FB) k_filter_obs(double* x, double* P, const d
     if (tid < 2) reinterpret_cast<double*>(clk)[tid] = sm->clk[tid];
 }
 
+// Streaming (one scan, KILO.cc:375-395): the samples that precede a bucket AND the bucket's own predict + constants in ONE launch —
+// k_filter_obs followed by k_predict_prepare(reset = 0) with the filter kept in shared memory in between. Same device functions
+// in the same order on the same values => bit-identical to the two launches.
+__global__ void __launch_bounds__(FB) k_obs_predict_prepare(const PredictArgs a, const lk_imu_meas* imu, const lk_kinimu_meas* kin,
+                                                            uint32_t n, lk_eskf_cfg cfg, double gravity, double acc_norm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ObsSmem* sm = reinterpret_cast<ObsSmem*>(smem_raw);
+    const int scan = a.scan_first, tid = threadIdx.x;
+    const StepInit in = a.init[scan];
+    double* xg = a.x + (size_t)scan * 36;
+    double* Pg = a.P + (size_t)scan * 900;
+    for (int e = tid; e < 900; e += FB) sm->f.P[e] = Pg[e];
+    if (tid < 36) sm->f.x[tid] = xg[tid];
+    if (tid < 2) sm->clk[tid] = reinterpret_cast<const double*>(a.clk + scan)[tid];
+    if (tid == 0) {
+        ScanStep st;
+        st.chunk_begin = in.chunk_begin; st.chunk_end = in.chunk_end;
+        st.pt_begin = in.pt_begin; st.pt_end = in.pt_end;
+        st.t_bucket = in.t_bucket; st.active = in.active; st.updated = 0; st.n_eff_last = 0; st.pad = 0;
+        a.step[scan] = st;
+        a.ticket[scan] = 0;
+    }
+    __syncthreads();
+    if (!in.active) return;
+    for (uint32_t i = 0; i < n; ++i) {  // predictUpdateImu / predictUpdateKinImu per sample (KILO.cc:235-314)
+        const double t = imu ? imu[i].stamp : kin[i].stamp;
+        block_predict_to(&sm->f, sm->clk, t, sm->F, sm->T, sm->Ps, a.Q);
+        if (imu) block_obs_imu<FB>(&sm->f, &sm->obs, imu + i, &cfg, gravity, acc_norm);
+        else block_obs_kinimu<FB>(&sm->f, &sm->obs, kin + i, &cfg, gravity, acc_norm);
+        if (tid == 0) sm->clk[1] = t;
+        __syncthreads();
+    }
+    block_predict_to(&sm->f, sm->clk, in.t_bucket, sm->F, sm->T, sm->Ps, a.Q);  // KILO.cc:110-115
+    for (int e = tid; e < 900; e += FB) Pg[e] = sm->f.P[e];
+    if (tid < 36) xg[tid] = sm->f.x[tid];
+    if (tid < 2) reinterpret_cast<double*>(a.clk + scan)[tid] = sm->clk[tid];
+    ScanConst* sc = a.sc + scan;
+    if (tid < 9) sc->R[tid] = sm->f.x[tid];
+    else if (tid < 12) sc->p[tid - 9] = sm->f.x[tid];
+    else if (tid < 24) {
+        const int ut[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+        const int q = (tid - 12) % 6, o = (tid < 18) ? 0 : 3;
+        const int i = ut[q][0] + o, j = ut[q][1] + o;
+        const double v = 0.5 * (sm->f.P[i * 30 + j] + sm->f.P[j * 30 + i]);
+        if (tid < 18) sc->Pth[q] = v; else sc->Ppp[q] = v;
+    }
+}
+
 // ESKF::updateByPoints (eskf.cc:91-113) from explicit rows: information-form sums, then the block solve.
 __global__ void __launch_bounds__(FB) k_update_by_points(double* x, double* P, uint32_t n, const double* h,
                                                          const double* z, const double* r) {
@@ -178,6 +226,7 @@ static void obs_attrs() {  // function attributes are per device
     static PerDeviceOnce once;
     if (once.first()) {
         cudaFuncSetAttribute(k_filter_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ObsSmem));
+        cudaFuncSetAttribute(k_obs_predict_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ObsSmem));
         cudaFuncSetAttribute(k_update_by_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ObsSmem));
     }
 }
@@ -193,6 +242,12 @@ void launch_update_by_points(double* x, double* P, uint32_t n, const double* h, 
                              cudaStream_t s) {
     obs_attrs();
     k_update_by_points<<<1, FB, sizeof(ObsSmem), s>>>(x, P, n, h, z, r);
+}
+
+void launch_obs_predict_prepare(const PredictArgs& a, const lk_imu_meas* imu, const lk_kinimu_meas* kin, uint32_t n,
+                                const lk_eskf_cfg& cfg, double gravity, double acc_norm, cudaStream_t s) {
+    obs_attrs();
+    k_obs_predict_prepare<<<1, FB, sizeof(ObsSmem), s>>>(a, imu, kin, n, cfg, gravity, acc_norm);
 }
 
 void launch_predict_prepare(const PredictArgs& a, cudaStream_t s) {

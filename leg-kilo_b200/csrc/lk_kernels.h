@@ -71,6 +71,8 @@ struct PredictArgs {
     int batch;       // scans in the range (grid.x)
 };
 void launch_predict_prepare(const PredictArgs& a, cudaStream_t s);
+void launch_obs_predict_prepare(const PredictArgs& a, const lk_imu_meas* imu, const lk_kinimu_meas* kin, uint32_t n,
+                                const lk_eskf_cfg& cfg, double gravity, double acc_norm, cudaStream_t s);
 
 // Plain ESKF::predict on `batch` filters with explicit dt (lk_predict).
 void launch_predict_dt(double* x, double* P, const double* Q, const double* dt, int batch, int prop_state,
