@@ -267,3 +267,74 @@ def test_map_sliding_rule_matches():
     keys1 = abi.parse_map_blob(r.map_export())[1]["key"]
     assert {tuple(x) for x in keys1.tolist()} == {tuple(x) for x in keys0[keep].tolist()}
     assert not r.map_slide([9.5, 1.0, 0.2])  # measured from the position of the last slide now
+
+
+def _clutter(n=24000, seed=77):
+    """Volumetric clutter with a thin slab and a flat sheet inside: roots fail the plane test, are cut into octants down to
+    max_layer, big leaves freeze — cut_octo_tree, the freeze rules and the all-children descent of build_single_residual."""
+    g = synth.rng(seed)
+    pw = np.concatenate([
+        g.uniform(-3, 3, (n // 2, 3)),
+        np.c_[g.uniform(-3, 3, (n // 4, 2)), 0.13 + 0.002 * g.standard_normal(n // 4)],
+        g.uniform(3, 5, (n // 4, 3)) * np.array([1, 1, 0.05])]).astype(np.float32)
+    pb = pw.copy()
+    pb[:, 2] -= 0.2
+    return pw, pb
+
+
+@pytest.mark.parametrize("cfg_over", [dict(), dict(voxel_size=0.4, max_layer=3, layer_init_num=(5, 4, 4, 3, 3), max_points_num=30)])
+def test_cluttered_map_and_descent_residuals_match(cfg_over):
+    """Octree subdivision (voxel_map.cc:139-183), frozen leaves (:125-129, :207-211) and residuals that come from the descent through
+    non-plane roots with the most probable plane winning (voxel_map.cc:412-424), then UpdateVoxelMap into that subdivided map —
+    also with a non-power-of-two voxel size, a deeper tree and other thresholds."""
+    cfg = dict(abi.CONFIGS["leg_fusion"], **cfg_over)
+    pw, pb = _clutter(n=24000 if not cfg_over else 70000)
+    G = synth.exp_so3([0.01, -0.02, 0.03])
+    kw = dict(R=G, rot_cov=np.diag([1e-6, 2e-6, 3e-6]), pos_cov=np.diag([4e-6, 5e-6, 6e-6]))
+    x0 = _moving_state()
+    clk = np.zeros(1, abi.CLOCK_DTYPE); clk["last_predict_time"] = 4.99; clk["last_update_time"] = 4.985
+    o, r = _pair(cfg, pw, pb, x0, clk, **kw)
+    st = mapcmp.compare_blobs(r.map_export(), o.map_export(), rtol=1e-7, pt_atol=0.0, var_rtol=1e-12)
+    assert st["interior"] > 50 and st["planes"] > 100
+    # scan points: map points seen again with noise, from the lidar frame of the moving prior (identity attitude, zero position)
+    g = synth.rng(5)
+    R, t = abi.extrinsics(cfg)
+    sel = g.choice(len(pw), 900, replace=False)
+    body = ((pw[sel].astype(np.float64) + 0.004 * g.standard_normal((900, 3))) - t) @ R
+    pts = np.c_[body, np.zeros(900)].astype(np.float32)
+    tt = 5.0
+    total = 0
+    for k in range(3):
+        ro = o.predict_update_point(tt, pts[k * 300:(k + 1) * 300]); rr = r.predict_update_point(tt, pts[k * 300:(k + 1) * 300])
+        assert ro["n_eff"] == rr["n_eff"] and ro["updated"] == rr["updated"]
+        total += rr["n_eff"]
+        np.testing.assert_allclose(ro["world"], rr["world"], rtol=0, atol=2e-6)
+        _same_filter(o, r, x0, tol=1e-9)
+        tt += 0.002
+    assert total > 100
+    mapcmp.compare_blobs(r.map_export(), o.map_export(), rtol=1e-6, pt_atol=1e-11, var_rtol=1e-8)
+
+
+def test_leaves_fill_up_and_freeze_identically():
+    """The same surface patch re-observed bucket after bucket until its leaves pass max_points_num: refit every 6th new point,
+    then the freeze (`>=` on a plane leaf at voxel_map.cc:205, `>` at :234 and in init_octo_tree :125) with the retained points
+    swapped away — counters, flags and planes of every node stay equal."""
+    cfg, pw, pb, scan = _scene("leg_fusion", half=4.0, wall=3.25, n_az=90)
+    x0 = _moving_state()
+    clk = np.zeros(1, abi.CLOCK_DTYPE); clk["last_predict_time"] = 0.99; clk["last_update_time"] = 0.99
+    o, r = _pair(cfg, pw, pb, x0, clk)
+    g = synth.rng(9)
+    base = scan[:160].copy()
+    t = 1.0
+    for k in range(14):
+        pts = base.copy()
+        pts[:, :3] += (0.003 * g.standard_normal((len(base), 3))).astype(np.float32)
+        ro = o.predict_update_point(t, pts); rr = r.predict_update_point(t, pts)
+        assert ro["n_eff"] == rr["n_eff"] > 100
+        _same_filter(o, r, x0, tol=1e-8)
+        t += 0.002
+    bo, br = o.map_export(), r.map_export()
+    st = mapcmp.compare_blobs(br, bo, rtol=1e-5, pt_atol=1e-10, var_rtol=1e-7)
+    _, _, nodes, aux, _ = abi.parse_map_blob(br)
+    frozen = ((nodes["flags"] & 4) == 0) & ((nodes["flags"] & 2) != 0)  # initialised, update_enable off
+    assert frozen.sum() > 10 and (aux["pts_count"][frozen] == 0).all()
