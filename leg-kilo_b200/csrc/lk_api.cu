@@ -93,7 +93,7 @@ struct lk_context {
     uint64_t total_pts = 0;
     uint32_t total_chunks = 0, n_steps = 0, max_chunk_pts = 0;
     std::vector<ChunkDesc> h_chunks, h_chunksL;
-    DevBuf pts, world, sc, step, partial, ticket;
+    DevBuf pts, world, sc, step, partial, ticket, fb_list, fb_cnt;
     // small per-call inputs / outputs travel as ONE packed copy each way (pinned staging blocks)
     DevBuf small_in, small_out, fx, fP, fQ, fclk;
     PinnedBuf h_small_in, h_small_out;
@@ -233,6 +233,8 @@ ResidualArgs residual_args(lk_context* c, const ChunkDesc* chunks) {
     a.clk = c->clk.as<lk_stream_clock>();
     a.n_eff = c->n_eff.as<uint32_t>();
     a.trace = c->trace_on ? c->trace.as<unsigned long long>() : nullptr;
+    a.fb_list = c->fb_list.as<uint16_t>();
+    a.fb_cnt = c->fb_cnt.as<uint32_t>();
     a.g = c->g;
     return a;
 }
@@ -316,7 +318,7 @@ int lk_destroy(lk_handle h) {
     DevBuf* bufs[] = {&h->pts, &h->world,
                       &h->sc, &h->step, &h->partial, &h->ticket, &h->small_in, &h->small_out, &h->fx, &h->fP, &h->fQ, &h->fclk, &h->dbg_ok, &h->dbg_h, &h->dbg_z, &h->dbg_R,
                       &h->dbg_key, &h->tmp, &h->trace, &h->ll, &h->Qc, &h->ins_pts, &h->ins_root, &h->ins_pend, &h->ins_touched,
-                      &h->ins_counters, &h->ins_list};
+                      &h->ins_counters, &h->ins_list, &h->fb_list, &h->fb_cnt};
     for (DevBuf* b : bufs) b->release();
     h->h_small_in.release();
     h->h_small_out.release();
@@ -625,6 +627,11 @@ static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P
     LK_CUDA(h, h->sc.ensure((size_t)batch * sizeof(ScanConst)));
     LK_CUDA(h, h->step.ensure((size_t)batch * sizeof(ScanStep)));
     LK_CUDA(h, h->partial.ensure(2 * std::max<size_t>(std::max(chunks.size(), chunksL.size()), 1) * PARTIAL_STRIDE * 8));
+    if (batch >= 2 || h->max_chunk_pts > 256) {  // the throughput family's per-chunk fallback lists
+        const size_t nch = std::max<size_t>(std::max(chunks.size(), chunksL.size()), 1);
+        LK_CUDA(h, h->fb_list.ensure(nch * S2_FB_WARPS * S2_FB_CAP * sizeof(uint16_t)));
+        LK_CUDA(h, h->fb_cnt.ensure(nch * S2_FB_WARPS * sizeof(uint32_t)));
+    }
     if (!h->ll.p) {
         LK_CUDA(h, h->ll.ensure(LL_BYTES));
         LK_CUDA(h, cudaMemsetAsync(h->ll.p, 0, LL_BYTES, h->stream));
@@ -994,8 +1001,9 @@ static int run_range_impl(lk_handle h, uint32_t first, uint32_t count, int iters
             // sharded (bitwise-reproducible sums)
             if (count >= 2 || h->max_chunk_pts > 256) {
                 launch_residual_stream2(ra, c1 - c0, s);
+                launch_residual_fallback(ra, c1 - c0, s);
                 launch_scan_tail(ra, first, count, s);
-                if (c1 > c0) ++h->acc_launches;
+                if (c1 > c0) h->acc_launches += 2;
             } else {
                 launch_residual(ra, c1 - c0, false, true, s);
             }

@@ -42,8 +42,13 @@ struct ResidualArgs {
     double* dbg_R;
     int32_t* dbg_key;
     unsigned long long* trace;  // optional %globaltimer stamps: 8 per block + 8 for the tail
+    // throughput family: the points whose home voxel gave no residual on the hot images, per chunk and warp in ballot order
+    // (chunk-relative indices), finished by k_residual_fallback with the full reference sequence
+    uint16_t* fb_list;  // [total_chunks][S2_FB_WARPS][S2_FB_CAP]
+    uint32_t* fb_cnt;   // [total_chunks][S2_FB_WARPS]
     Globals g;
 };
+constexpr uint32_t S2_FB_WARPS = 6, S2_FB_CAP = 352;
 
 // single: every chunk of the launch holds at most 256 points (one point per thread, one pass); otherwise blocks make
 // several passes over their chunk
@@ -51,6 +56,7 @@ void launch_residual(const ResidualArgs& a, uint32_t n_chunks, bool debug, bool 
 // throughput family: pipelined residual pass (lk_stream2.cu) writing one partial row per chunk, then the per-scan
 // solve for scans [scan_first, scan_first + n_scans) (lk_residual.cu)
 void launch_residual_stream2(const ResidualArgs& a, uint32_t n_chunks, cudaStream_t s);
+void launch_residual_fallback(const ResidualArgs& a, uint32_t n_chunks, cudaStream_t s);
 void launch_scan_tail(const ResidualArgs& a, uint32_t scan_first, uint32_t n_scans, cudaStream_t s);
 
 struct PredictArgs {

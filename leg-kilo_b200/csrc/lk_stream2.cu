@@ -33,14 +33,13 @@ struct Probe {  // what stage B leaves for stage C
 template <int S2_WARPS>
 struct S2Smem {
     static constexpr int FB_CAP = ((S2_MAXPTS / 32 + S2_WARPS - 1) / S2_WARPS) * 32;
+    static_assert(S2_WARPS == (int)S2_FB_WARPS && FB_CAP == (int)S2_FB_CAP && S2_MAXPTS <= 0x8000, "fallback list layout (lk_kernels.h)");
     __align__(16) unsigned char st[S2_WARPS][2][S2_STAGE_BYTES];
     double slice[S2_WARPS * 32];
     // A = sum h^T h / R (21 terms) of every thread, [term][thread]: at 168 registers the compiler kept these in local memory,
     // whose footprint (two blocks x 192 threads) does not fit the 28 KB of L1 left beside the stages — every reload was an L2
     // round trip (local-load hit rate 1 % in ncu). Conflict-free 8-byte accesses, no synchronisation: a thread owns its column.
     double accA[21][S2_WARPS * 32];
-    uint16_t fb[S2_WARPS][FB_CAP];  // chunk-relative point indices
-    uint32_t nfb[S2_WARPS];
     ScanConst sc;
 };
 static_assert(2 * (sizeof(S2Smem<6>) + 1024) <= 228 * 1024, "two blocks per SM");
@@ -65,11 +64,12 @@ __device__ __forceinline__ void gather_triple(int r, const unsigned char* hot_su
 
 // The plane branch of build_single_residual (voxel_map.cc:370-411) + the row of KILO.cc:192-209 on a staged hot image:
 // sigma_plane = a^T Scc a - 2 a^T v + s (lk_device.cuh: HotRec). Everything else as eval_plane.
-__device__ __forceinline__ bool eval_plane_hot(const unsigned char* slot, const PointCtx& pc, const ScanConst& sc, const Globals& g,
-                                               Row& row) {
+// Returns 0 = row produced, 1 = the node holds no plane (octree descent needed), 2 = a plane, but the point is gated out.
+__device__ __forceinline__ int eval_plane_hot(const unsigned char* slot, const PointCtx& pc, const ScanConst& sc, const Globals& g,
+                                              Row& row) {
     const double* q = reinterpret_cast<const double*>(slot);
     const float2 dr = *reinterpret_cast<const float2*>(q + 16);
-    if (dr.y < 0.0f) return false;  // no plane in this node
+    if (dr.y < 0.0f) return 1;  // no plane in this node
     const double2 v0 = *reinterpret_cast<const double2*>(q), v1 = *reinterpret_cast<const double2*>(q + 2),
                   v2 = *reinterpret_cast<const double2*>(q + 4);
     const double c0 = v0.x, c1 = v0.y, c2 = v1.x, n0 = v1.y, n1 = v2.x, n2 = v2.y;
@@ -78,7 +78,7 @@ __device__ __forceinline__ bool eval_plane_hot(const unsigned char* slot, const 
     const double ax = pc.pwx - c0, ay = pc.pwy - c1, az = pc.pwz - c2;
     const float dc = (float)(ax * ax + ay * ay + az * az);
     const float rd = sqrtf(__fsub_rn(dc, __fmul_rn(dis, dis)));
-    if (!((double)rd <= 3.0 * (double)dr.y)) return false;
+    if (!((double)rd <= 3.0 * (double)dr.y)) return 2;
     const double sigma_pl = quad_sym3(q + 6, ax, ay, az) - 2.0 * (ax * q[12] + ay * q[13] + az * q[14]) + q[15];
     const double qx = sc.R[0] * n0 + sc.R[3] * n1 + sc.R[6] * n2;
     const double qy = sc.R[1] * n0 + sc.R[4] * n1 + sc.R[7] * n2;
@@ -99,11 +99,11 @@ __device__ __forceinline__ bool eval_plane_hot(const unsigned char* slot, const 
     if (lhs < rhs * (1.0 - 1e-12)) pass = true;
     else if (lhs > rhs * (1.0 + 1e-12)) pass = false;
     else pass = (double)dis < g.sigma_num * sqrt(sigma_l);
-    if (!pass) return false;
+    if (!pass) return 2;
     row.h[0] = hx; row.h[1] = hy; row.h[2] = hz; row.h[3] = n0; row.h[4] = n1; row.h[5] = n2;
     row.z = -(double)(float)s;
     row.R = g.ratio * (sigma_pl + body);
-    return true;
+    return 0;
 }
 
 // accumulate_row (lk_pass.cuh) with the 21 terms of A in shared memory: same products, same order, same contraction.
@@ -156,6 +156,8 @@ __global__ void __launch_bounds__(S2_THREADS, 2) k_residual_stream2(const __grid
 #pragma unroll
     for (int i = 0; i < 8; ++i) rest[i] = 0.0;
     uint32_t nfbw = 0;
+    // this warp's list of points to finish with the full reference sequence (k_residual_fallback), in ballot order
+    uint16_t* fbw = a.fb_list + ((size_t)(a.chunk_first + blockIdx.x) * S2_FB_WARPS + (uint32_t)warp) * S2_FB_CAP;
 
     // group i of this warp starts at point (warp + i * S2_WARPS) * 32
     auto first_of = [&](uint32_t i) { return ((uint32_t)warp + i * (uint32_t)S2_WARPS) * 32u; };
@@ -215,50 +217,36 @@ __global__ void __launch_bounds__(S2_THREADS, 2) k_residual_stream2(const __grid
             const unsigned char* slot = &sm->st[warp][i & 1u][0] + (size_t)lane * S2_STRIDE;
             const int root = *reinterpret_cast<const int*>(slot + S2_SLOT_ROOT);
             bool fail = false;
+            int why = 0;
             if (root >= 0) {
                 const float4 pt = *reinterpret_cast<const float4*>(slot + S2_SLOT_PT);
                 PointCtx pc;
                 float lx, ly, lz;
                 prepare_point(pt, sc, g, pc, lx, ly, lz);
                 Row row;
-                if (eval_plane_hot(slot, pc, sc, g, row)) accumulate_row_sm<S2_THREADS>(row, colA, rest);
-                else fail = true;  // not a plane here, or gated out: finished below with the full reference sequence
+                const int rc = eval_plane_hot(slot, pc, sc, g, row);
+                if (rc == 0) accumulate_row_sm<S2_THREADS>(row, colA, rest);
+                else { fail = true; why = rc; }  // finished by k_residual_fallback
             }
             const uint32_t m = __ballot_sync(0xffffffffu, fail);
-            if (fail) sm->fb[warp][nfbw + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(first_of(i) + (uint32_t)lane);
+            if (fail) fbw[nfbw + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((first_of(i) + (uint32_t)lane) | (why == 2 ? 0x8000u : 0u));
             nfbw += __popc(m);
         }
         __syncwarp();  // the stage is rewritten by the gather issued next round
         pr_c = pr_b;
     }
     cp_async_wait_group<0>();
-    if (lane == 0) sm->nfb[warp] = nfbw;
-    // the rare rows below and the reduction work on a register image (layout of lk_kernels.h: A | b | sum R | count)
+    if (lane == 0) a.fb_cnt[(size_t)(a.chunk_first + blockIdx.x) * S2_FB_WARPS + (uint32_t)warp] = nfbw;
+    // register image for the reduction (layout of lk_device.cuh: A | b | sum R | count)
     double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < 21; ++i) acc[i] = colA[i * S2_THREADS];
 #pragma unroll
     for (int i = 0; i < 6; ++i) acc[ACC_B + i] = rest[i];
     acc[ACC_SUMR] = rest[6];
     acc[ACC_CNT] = rest[7];
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-        if (i != ACC_SUMR && i != ACC_CNT && !(i < 21) && !(i >= ACC_B && i < ACC_B + 6)) acc[i] = 0.0;
-    __syncthreads();
-    {
-        uint32_t cnt[S2_WARPS], total = 0;
-#pragma unroll
-        for (int w2 = 0; w2 < S2_WARPS; ++w2) { cnt[w2] = sm->nfb[w2]; total += cnt[w2]; }
-        for (uint32_t e = (uint32_t)tid; e < total; e += S2_THREADS) {
-            uint32_t k = e;
-            int w2 = 0;
-#pragma unroll
-            for (int t = 0; t < S2_WARPS - 1; ++t)
-                if (w2 == t && k >= cnt[t]) { k -= cnt[t]; w2 = t + 1; }
-            Row row;
-            if (point_row(__ldg(pts + sm->fb[w2][k]), sc, mv, g, row, nullptr)) accumulate_row(row, acc);
-        }
-    }
     const double tot = warp_transpose_sum(acc, lane);
     sm->slice[warp * 32 + lane] = tot;
     __syncthreads();
@@ -267,6 +255,70 @@ __global__ void __launch_bounds__(S2_THREADS, 2) k_residual_stream2(const __grid
 #pragma unroll
         for (int w2 = 0; w2 < S2_WARPS; ++w2) v += sm->slice[w2 * 32 + tid];
         a.partial[(size_t)(a.chunk_first + blockIdx.x) * PARTIAL_STRIDE + tid] = v;
+    }
+}
+
+// The points the pipelined kernel could not finish on the hot images — no plane in the home node (octree descent, voxel_map.cc:412-424)
+// or gated out at home (then the one neighbour voxel, KILO.cc:156-178) — with the full reference sequence (point_row), one block
+// per chunk, entry e of the warp-major concatenation of the chunk's lists on thread e. A chain of dependent cold reads per point:
+// it wants many points in flight and few registers live, which is why it is its own kernel (inside the pipelined kernel it cost 30 %
+// of the time at 12 warps per SM). Adds its sums to the chunk's partial row: same stream, after the kernel that wrote the row.
+// The second half of KILO.cc:154-178 alone: the ONE neighbour voxel, for a point whose home voxel is known to have failed.
+__device__ __forceinline__ bool point_row_neighbour(float4 pt, const ScanConst& sc, const MapView& mv, const Globals& g, Row& row) {
+    PointCtx pc;
+    float lx, ly, lz;
+    prepare_point(pt, sc, g, pc, lx, ly, lz);
+    const int kx = (int)lx, ky = (int)ly, kz = (int)lz;
+    int nx, ny, nz;
+    neighbour_key(g, lx, ly, lz, kx, ky, kz, nx, ny, nz);
+    if (nx == kx && ny == ky && nz == kz) return false;  // the same voxel again: the same failure
+    const int root = map_find(mv.slots, mv.hash_mask, nx, ny, nz);
+    if (root < 0) return false;
+    PlaneRec r;
+    load_plane(mv.nodes + root, r);
+    return eval_record(mv.nodes, r, pc, sc, g, row);
+}
+
+constexpr int FB_THREADS = 128;
+__global__ void __launch_bounds__(FB_THREADS, 4) k_residual_fallback(const __grid_constant__ ResidualArgs a) {
+    __shared__ ScanConst s_sc;
+    __shared__ double s_slice[(FB_THREADS / 32) * 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t c = a.chunk_first + blockIdx.x;
+    uint32_t cnt[S2_FB_WARPS], total = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < S2_FB_WARPS; ++w) { cnt[w] = __ldg(a.fb_cnt + (size_t)c * S2_FB_WARPS + w); total += cnt[w]; }
+    if (total == 0) return;  // the same for every thread of the block
+    const ChunkDesc cd = a.chunks[c];
+    if (tid < (int)(sizeof(ScanConst) / sizeof(double)))
+        reinterpret_cast<double*>(&s_sc)[tid] = reinterpret_cast<const double*>(a.sc + cd.scan)[tid];
+    __syncthreads();
+    const MapView mv = {a.slots, a.hash_mask, a.nodes};
+    const float4* __restrict__ pts = a.pts + cd.start;
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+    for (uint32_t e = (uint32_t)tid; e < total; e += FB_THREADS) {
+        uint32_t k = e, w2 = 0;
+#pragma unroll
+        for (uint32_t t = 0; t < S2_FB_WARPS - 1; ++t)
+            if (w2 == t && k >= cnt[t]) { k -= cnt[t]; w2 = t + 1; }
+        const uint32_t ent = __ldg(a.fb_list + ((size_t)c * S2_FB_WARPS + w2) * S2_FB_CAP + k);
+        const float4 pt = __ldg(pts + (ent & 0x7fffu));
+        Row row;
+        // bit 15: the home voxel is a plane that gated the point out — build_single_residual left is_success false there
+        // (voxel_map.cc:370-411), so only the neighbour voxel is left to try; otherwise the whole sequence, descent included
+        const bool ok = (ent & 0x8000u) ? point_row_neighbour(pt, s_sc, mv, a.g, row) : point_row(pt, s_sc, mv, a.g, row, nullptr);
+        if (ok) accumulate_row(row, acc);
+    }
+    const double tot = warp_transpose_sum(acc, lane);
+    s_slice[warp * 32 + lane] = tot;
+    __syncthreads();
+    if (tid < 32) {
+        double v = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < FB_THREADS / 32; ++w2) v += s_slice[w2 * 32 + tid];
+        a.partial[(size_t)c * PARTIAL_STRIDE + tid] += v;
     }
 }
 
@@ -280,6 +332,11 @@ void launch_residual_stream2(const ResidualArgs& a, uint32_t n_chunks, cudaStrea
         cudaFuncSetAttribute(k_residual_stream2<192>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     }
     k_residual_stream2<192><<<n_chunks, 192, sizeof(S2Smem<6>), s>>>(a);
+}
+
+void launch_residual_fallback(const ResidualArgs& a, uint32_t n_chunks, cudaStream_t s) {
+    if (n_chunks == 0) return;
+    k_residual_fallback<<<n_chunks, FB_THREADS, 0, s>>>(a);
 }
 
 }  // namespace lk
