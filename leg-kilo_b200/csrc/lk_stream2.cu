@@ -280,7 +280,7 @@ __device__ __forceinline__ bool point_row_neighbour(float4 pt, const ScanConst& 
 }
 
 constexpr int FB_THREADS = 128;
-__global__ void __launch_bounds__(FB_THREADS, 4) k_residual_fallback(const __grid_constant__ ResidualArgs a) {
+__global__ void __launch_bounds__(FB_THREADS, 8) k_residual_fallback(const __grid_constant__ ResidualArgs a) {
     __shared__ ScanConst s_sc;
     __shared__ double s_slice[(FB_THREADS / 32) * 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
