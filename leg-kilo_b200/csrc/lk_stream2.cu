@@ -264,7 +264,8 @@ __global__ void __launch_bounds__(S2_THREADS, 2) k_residual_stream2(const __grid
 // it wants many points in flight and few registers live, which is why it is its own kernel (inside the pipelined kernel it cost 30 %
 // of the time at 12 warps per SM). Adds its sums to the chunk's partial row: same stream, after the kernel that wrote the row.
 // The second half of KILO.cc:154-178 alone: the ONE neighbour voxel, for a point whose home voxel is known to have failed.
-__device__ __forceinline__ bool point_row_neighbour(float4 pt, const ScanConst& sc, const MapView& mv, const Globals& g, Row& row) {
+__device__ __forceinline__ bool point_row_neighbour(float4 pt, const ScanConst& sc, const MapView& mv, const HotRec* __restrict__ hot,
+                                                    const Globals& g, Row& row) {
     PointCtx pc;
     float lx, ly, lz;
     prepare_point(pt, sc, g, pc, lx, ly, lz);
@@ -274,6 +275,9 @@ __device__ __forceinline__ bool point_row_neighbour(float4 pt, const ScanConst& 
     if (nx == kx && ny == ky && nz == kz) return false;  // the same voxel again: the same failure
     const int root = map_find(mv.slots, mv.hash_mask, nx, ny, nz);
     if (root < 0) return false;
+    // a plane in the neighbour root (the common case): its hot image decides, as in the pipelined kernel; otherwise the descent
+    const int rc = eval_plane_hot(reinterpret_cast<const unsigned char*>(hot + root), pc, sc, g, row);
+    if (rc != 1) return rc == 0;
     PlaneRec r;
     load_plane(mv.nodes + root, r);
     return eval_record(mv.nodes, r, pc, sc, g, row);
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(FB_THREADS, 8) k_residual_fallback(const __gri
         Row row;
         // bit 15: the home voxel is a plane that gated the point out — build_single_residual left is_success false there
         // (voxel_map.cc:370-411), so only the neighbour voxel is left to try; otherwise the whole sequence, descent included
-        const bool ok = (ent & 0x8000u) ? point_row_neighbour(pt, s_sc, mv, a.g, row) : point_row(pt, s_sc, mv, a.g, row, nullptr);
+        const bool ok = (ent & 0x8000u) ? point_row_neighbour(pt, s_sc, mv, a.hot, a.g, row) : point_row(pt, s_sc, mv, a.g, row, nullptr);
         if (ok) accumulate_row(row, acc);
     }
     const double tot = warp_transpose_sum(acc, lane);
