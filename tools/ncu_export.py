@@ -29,5 +29,8 @@ export(os.path.join(ROOT, "gpurun_out/r2_fused.ncu-rep"), "k_scan_fused", os.pat
        "leg_fusion_b1 (bench.py default: one 28.8k-point scan x 3 iterations per launch, ring of 512 scans, 1.2M-voxel map)", 304 * 28792 * 3, traffic)
 export(os.path.join(ROOT, "gpurun_out/r2_stream2.ncu-rep"), "k_residual_stream2", os.path.join(ROOT, "profiles/r2_ncu_k_residual_stream2.csv"),
        "synth100k_b1024 shard (128 scans x 102 399 points per launch, 10M-voxel map)", 304 * 128 * 102399, traffic)
+if os.path.exists(os.path.join(ROOT, "gpurun_out/r2_fallback.ncu-rep")):
+    export(os.path.join(ROOT, "gpurun_out/r2_fallback.ncu-rep"), "k_residual_fallback", os.path.join(ROOT, "profiles/r2_ncu_k_residual_fallback.csv"),
+           "synth100k_b1024 shard: the ~5 % of the launch's points the hot-image pass could not finish (no algorithmic-byte figure of its own: its points are counted in k_residual_stream2's 304 B)", 0, traffic)
 json.dump(traffic, open(os.path.join(ROOT, "profiles/r2_traffic.json"), "w"), indent=1)
 print(json.dumps(traffic, indent=1))
