@@ -420,137 +420,4 @@ __device__ __forceinline__ void cached_points_pass(CachedPassSmem<NTHREADS>* ps,
 }
 
 
-// =================================================================================================
-// Throughput variant: every warp streams its own 32-point groups of the block's chunk with no
-// block-wide barrier inside the loop; records are staged by warp-cooperative 16-byte async copies
-// (two 256-byte records per warp instruction: 4 cache lines instead of 32); points that fail at
-// home only remember their neighbour key and are finished in bulk after the loop.
-// =================================================================================================
-template <int NTHREADS, int MAXPTS>
-struct StreamSmem {
-    __align__(16) unsigned char tile[NTHREADS * TILE_STRIDE];  // 32 slots per warp
-    struct Fallback {
-        uint32_t idx;
-    } fb[MAXPTS];
-    uint32_t n_fb;
-    uint32_t pad[3];
-};
-
-__device__ __forceinline__ bool eval_node(const MapView& mv, const PlaneRec& r, const PointCtx& pc, const ScanConst& sc,
-                                          const Globals& g, Row& row) {
-    double prob = 0.0;
-    if (r.flags & LK_NODE_IS_PLANE) return eval_plane(r, pc, sc, g, false, prob, row);
-    const uint32_t cmask = (r.flags >> LK_NODE_CHILDMASK_SHIFT) & 0xffu;
-    if (g.max_layer >= 1 && r.child_base >= 0 && cmask) return visit_subtree(mv.nodes, r.child_base, cmask, &pc, &sc, &g, &prob, &row);
-    return false;
-}
-
-// eval_plane reading the staged record field by field (no 29-double register image): centre and
-// normal first, the cheap float gate, and only then the 21 plane-covariance terms.
-__device__ __forceinline__ bool eval_plane_staged(const unsigned char* slot, const PointCtx& pc, const ScanConst& sc,
-                                                  const Globals& g, Row& row) {
-    const double* q = reinterpret_cast<const double*>(slot);
-    const double2 v0 = *reinterpret_cast<const double2*>(q), v1 = *reinterpret_cast<const double2*>(q + 2),
-                  v2 = *reinterpret_cast<const double2*>(q + 4);
-    const double c0 = v0.x, c1 = v0.y, c2 = v1.x, n0 = v1.y, n1 = v2.x, n2 = v2.y;
-    const float2 dr = *reinterpret_cast<const float2*>(q + 27);
-    const double s = n0 * pc.pwx + n1 * pc.pwy + n2 * pc.pwz + (double)dr.x;
-    const float dis = (float)fabs(s);
-    const double ax = pc.pwx - c0, ay = pc.pwy - c1, az = pc.pwz - c2;
-    const float dc = (float)(ax * ax + ay * ay + az * az);
-    const float rd = sqrtf(__fsub_rn(dc, __fmul_rn(dis, dis)));
-    if (!((double)rd <= 3.0 * (double)dr.y)) return false;
-    const double J0 = ax, J1 = ay, J2 = az, J3 = -n0, J4 = -n1, J5 = -n2;
-    const double* pv = q + 6;
-    double sigma_pl = J0 * (pv[0] * J0 + 2.0 * (pv[1] * J1 + pv[2] * J2 + pv[3] * J3 + pv[4] * J4 + pv[5] * J5));
-    sigma_pl += J1 * (pv[6] * J1 + 2.0 * (pv[7] * J2 + pv[8] * J3 + pv[9] * J4 + pv[10] * J5));
-    sigma_pl += J2 * (pv[11] * J2 + 2.0 * (pv[12] * J3 + pv[13] * J4 + pv[14] * J5));
-    sigma_pl += J3 * (pv[15] * J3 + 2.0 * (pv[16] * J4 + pv[17] * J5));
-    sigma_pl += J4 * (pv[18] * J4 + 2.0 * (pv[19] * J5));
-    sigma_pl += J5 * (pv[20] * J5);
-    const double qx = sc.R[0] * n0 + sc.R[3] * n1 + sc.R[6] * n2;
-    const double qy = sc.R[1] * n0 + sc.R[4] * n1 + sc.R[7] * n2;
-    const double qz = sc.R[2] * n0 + sc.R[5] * n1 + sc.R[8] * n2;
-    const double hx = pc.piy * qz - pc.piz * qy, hy = pc.piz * qx - pc.pix * qz, hz = pc.pix * qy - pc.piy * qx;
-    const double wx = g.Re[0] * qx + g.Re[3] * qy + g.Re[6] * qz;
-    const double wy = g.Re[1] * qx + g.Re[4] * qy + g.Re[7] * qz;
-    const double wz = g.Re[2] * qx + g.Re[5] * qy + g.Re[8] * qz;
-    const double uw = pc.pbx * wx + pc.pby * wy + pc.pbz * wz;
-    const double ww = wx * wx + wy * wy + wz * wz;
-    const double uw2 = uw * uw / pc.r2;
-    const double body = (double)g.rv * uw2 + pc.range2 * g.dv * (ww - uw2);
-    const double state = quad_sym3(sc.Pth, hx, hy, hz) + quad_sym3(sc.Ppp, n0, n1, n2);
-    const double sigma_l = sigma_pl + body + state;
-    const double lhs = (double)dis * (double)dis;
-    const double rhs = g.sigma_num * g.sigma_num * sigma_l;
-    bool pass;
-    if (lhs < rhs * (1.0 - 1e-12)) pass = true;
-    else if (lhs > rhs * (1.0 + 1e-12)) pass = false;
-    else pass = (double)dis < g.sigma_num * sqrt(sigma_l);
-    if (!pass) return false;
-    row.h[0] = hx; row.h[1] = hy; row.h[2] = hz; row.h[3] = n0; row.h[4] = n1; row.h[5] = n2;
-    row.z = -(double)(float)s;
-    row.R = g.ratio * (sigma_pl + body);
-    return true;
-}
-
-template <int NTHREADS, int MAXPTS>
-__device__ __forceinline__ void block_points_stream(StreamSmem<NTHREADS, MAXPTS>* ss, const float4* __restrict__ pts,
-                                                    uint32_t count, const ScanConst& sc, const MapView& mv, const Globals& g,
-                                                    double (&acc)[32]) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = NTHREADS / 32;
-    unsigned char* wtile = ss->tile + (size_t)warp * 32 * TILE_STRIDE;
-    const int half = lane >> 4, sub = lane & 15;
-    float4 pt_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (warp * 32 + lane < count) pt_next = __ldg(pts + warp * 32 + lane);
-    for (uint32_t g0 = warp * 32; g0 < count; g0 += NW * 32) {
-        const uint32_t i = g0 + lane;
-        const bool active = i < count;
-        const float4 pt = pt_next;
-        if (i + NW * 32 < count) pt_next = __ldg(pts + i + NW * 32);  // next group's point: off the critical path
-        PointCtx pc;
-        float lx = 0, ly = 0, lz = 0;
-        int kx = 0, ky = 0, kz = 0, root = -1;
-        if (active) {
-            prepare_point(pt, sc, g, pc, lx, ly, lz);
-            kx = (int)lx; ky = (int)ly; kz = (int)lz;
-            const uint32_t ih = hash_key(kx, ky, kz) & mv.hash_mask;
-            root = resolve_pair(mv.slots, mv.hash_mask, ih, load_pair(mv.slots, ih), kx, ky, kz);
-        }
-        // cooperative gather: instruction j moves records of lanes 2j and 2j+1 (16 lanes x 16 B each)
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int r = __shfl_sync(0xffffffffu, root, 2 * j + half);
-            if (r >= 0) cp_async16(wtile + (size_t)(2 * j + half) * TILE_STRIDE + sub * 16,
-                                   reinterpret_cast<const unsigned char*>(mv.nodes + r) + sub * 16);
-        }
-        cp_async_wait_all();
-        __syncwarp();
-        if (root >= 0) {
-            const unsigned char* slot = wtile + (size_t)lane * TILE_STRIDE;
-            const uint32_t flags = *reinterpret_cast<const uint32_t*>(slot + 224);
-            Row row;
-            if ((flags & LK_NODE_IS_PLANE) && eval_plane_staged(slot, pc, sc, g, row)) {
-                accumulate_row(row, acc);
-            } else {
-                // not a plane here, or gated out: the point is finished in bulk with the full reference
-                // sequence (home octree descent, then the ONE neighbour voxel of KILO.cc:156-178)
-                const uint32_t e = atomicAdd(&ss->n_fb, 1u);
-                ss->fb[e].idx = i;
-            }
-        }
-        __syncwarp();  // the tile is rewritten by the next group
-    }
-    __syncthreads();
-    const uint32_t n_fb = ss->n_fb;
-    for (uint32_t e = tid; e < n_fb; e += NTHREADS) {
-        Row row;
-        if (point_row(__ldg(pts + ss->fb[e].idx), sc, mv, g, row, nullptr)) accumulate_row(row, acc);
-    }
-    __syncthreads();
-    if (tid == 0) ss->n_fb = 0;
-}
-
 }  // namespace lk
