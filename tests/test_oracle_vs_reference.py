@@ -338,3 +338,36 @@ def test_leaves_fill_up_and_freeze_identically():
     _, _, nodes, aux, _ = abi.parse_map_blob(br)
     frozen = ((nodes["flags"] & 4) == 0) & ((nodes["flags"] & 2) != 0)  # initialised, update_enable off
     assert frozen.sum() > 10 and (aux["pts_count"][frozen] == 0).all()
+
+
+from hypothesis import HealthCheck, given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+
+@settings(max_examples=8, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(seed=st.integers(0, 10**6), kin=st.booleans(), cfg_name=st.sampled_from(["leg_fusion", "hilti", "nclt", "diter"]),
+       voxel=st.sampled_from([0.5, 0.4, 0.25]), sigma=st.sampled_from([3.0, 2.0]))
+def test_random_streaming_frames_match(seed, kin, cfg_name, voxel, sigma):
+    """Randomised: dataset config (extrinsics), voxel size, gate width, observation mode, scene size, pose and sample noise — one
+    KILO::process frame after BuildVoxelMap, reference vs oracle, fed in the reference's own sorted order."""
+    cfg = dict(abi.CONFIGS[cfg_name], voxel_size=voxel, sigma_num=sigma)
+    g = np.random.default_rng(seed)
+    R, t = abi.extrinsics(cfg)
+    half = float(g.uniform(3.0, 6.0))
+    sc = synth.BoxScene(ground_half_extent=half, wall=half - 0.75)
+    pw, pb = sc.map_points(ext_R=R, ext_t=t, stream=int(seed % 1000) + 1)
+    x0 = _moving_state()
+    x0["vel"][0] = g.uniform(-0.5, 0.5, 3)
+    clk = np.zeros(1, abi.CLOCK_DTYPE); clk["last_predict_time"] = 7.995; clk["last_update_time"] = 7.995
+    o, r = _pair(cfg, pw, pb, x0, clk, imu_mode_only=not kin)
+    rv, tv = synth.random_poses(1, 3e-3, 0.03, stream=int(seed % 997) + 3)
+    scan = sc.scan(rotvec=rv[0], trans=tv[0], ext_R=R, ext_t=t, blind=cfg["blind"], stream=int(seed % 991) + 5, n_rings=8, n_az=100,
+                   fov_deg=(-15.0, 15.0), streaming=True)
+    meas = (synth.kinimu_stream if kin else synth.imu_stream)(7.996, 8.13, stream=int(seed % 89) + 7)
+    out = r.process(8.0, 8.1, scan, **{"kin" if kin else "imu": meas})
+    assert out["ok"]
+    ro = o.process_scan(8.0, out["body"], **{"kin" if kin else "imu": meas})
+    assert ro["n_eff"] == out["n_eff"]
+    np.testing.assert_allclose(ro["world"], out["world"], rtol=0, atol=3e-6)
+    _same_filter(o, r, x0, tol=1e-8)
+    mapcmp.compare_blobs(r.map_export(), o.map_export(), rtol=1e-5, pt_atol=1e-10, var_rtol=1e-7)
