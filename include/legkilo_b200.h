@@ -186,7 +186,7 @@ int lk_state_default(lk_state* x);
 
 /* Page-locked host memory (cudaHostAlloc / cudaFreeHost). A one-scan lk_scan_update whose `pts` and
  * `pts_world_out` live in page-locked memory (from here or cudaHostRegister) runs in DIRECT mode: nothing
- * is staged, the kernel reads the points and stores the world cloud / filter in place (DESIGN.md 3.5). */
+ * is staged, the kernel reads the points and stores the world cloud / filter in place (DESIGN.md 3.7). */
 int lk_host_alloc(void** p, size_t bytes);
 int lk_host_free(void* p);
 /* Tuning / diagnostic knobs by name. Results never depend on them beyond floating-point summation order.
@@ -198,6 +198,10 @@ int lk_host_free(void* p);
  *                 next scan's blocks run their prologue while the previous scan's last blocks drain
  *   "coop_launch" 1 = launch the fused kernel through cudaLaunchCooperativeKernel (co-residency checked by the
  *                 driver; for devices shared with OTHER processes, see INTEGRATION.md "Sharing a device")
+ *   "fast_insert" 1 (default) UpdateVoxelMap of a bucket of <= 4096 points takes two launches instead of five
+ *   "fused_insert" 0 (default); 1 = a streaming scan (update_map) runs entirely inside ONE persistent kernel, the map
+ *                 insert included (currently slower than the per-bucket kernels)
+ *   "slim_p"      1 (default) blocks that never read the full covariance load only the strip they need (fused kernel)
  *   "kernel_timing", "trace", "gather_mode": measurement / debugging aids */
 int lk_set_param(lk_handle h, const char* name, double value);
 

@@ -1,13 +1,20 @@
-// lk_stream2.cu — throughput family of the residual pass, double-buffered: every warp streams its 32-point
-// groups of the block's chunk through a 3-deep software pipeline
-//     points(i+3) | key + root-table probe(i+2) | record gather(i+1) -> shared stage | gates + row(i)
-// so that, while a group is evaluated from shared memory (voxel_map.cc:363-411, KILO.cc:187-210), the next
-// group's 32 plane records are already in flight (16 cooperative 16-byte async copies, two records per warp
-// instruction) and the one after has its probe and its points in flight. 6 warps x 2 stages per block,
-// 2 blocks per SM, 168 registers (no spills). Points that fail at their home plane are listed per warp
-// (ballot order) and finished by the whole block in warp-major order with the full reference sequence
-// (KILO.cc:156-178), so the per-chunk sums are bitwise reproducible. One partial row per chunk; the per-scan
-// solve follows as its own kernel (lk_residual.cu: k_scan_tail).
+// lk_stream2.cu — throughput family of the residual pass (calls with >= 2 scans), two kernels per iteration:
+//
+// k_residual_stream2: every warp streams its 32-point groups of the block's chunk through a 3-deep software pipeline
+//     points(i+3) | key + root-table probe(i+2) | hot-record gather(i+1) -> shared stage | gates + row(i)
+// so that, while a group is evaluated from shared memory (voxel_map.cc:363-411, KILO.cc:187-210), the next group's 32 hot
+// plane images (lk_device.cuh: HotRec, 144 bytes each) are already in flight (11 cooperative 16-byte async-copy instructions, three
+// records each) and the one after has its probe and its points in flight. The 21 terms of A = sum h^T h / R accumulate in shared
+// memory, one column per thread. 6 warps x 2 stages per block, 2 blocks per SM, 132 registers, no spills. Points the hot image
+// cannot finish — no plane in the home node, or gated out by it — are appended per chunk and warp, in ballot order, to a list in
+// global memory.
+//
+// k_residual_fallback: one block per chunk finishes that list with the full reference sequence (home octree descent, then the ONE
+// neighbour voxel, KILO.cc:156-178) — or only the neighbour half when the list entry says a home plane gated the point out — in
+// the warp-major order of the lists, and adds its sums to the chunk's partial row. Deterministic order in both kernels, so the
+// per-chunk sums are bitwise reproducible and do not depend on how a batch is sharded.
+//
+// One partial row per chunk; the per-scan solve follows as its own kernel (lk_residual.cu: k_scan_tail).
 #include <algorithm>
 
 #include "lk_kernels.h"
