@@ -198,10 +198,10 @@ void fill_globals(lk_context* c, const double* extR, const double* extT) {
 // of how a batch is sharded across GPUs (SURVEY §4 multi-GPU invariant).
 //   latency family (one scan per call): buckets up to 148 x 256 points use one point per thread (256-point
 //     chunks, one per SM: the fused kernel); larger ones the throughput family's chunks;
-//   throughput family (>= 2 scans per call): 1 920-point chunks as soon as a bucket exceeds 2 048 points —
-//     every warp then streams 10 groups and the per-chunk reduce is amortised.
+//   throughput family (>= 2 scans per call): 3 840-point chunks as soon as a bucket exceeds 2 048 points —
+//     every warp then streams 20 groups and the per-chunk reduce is amortised.
 constexpr uint32_t LATENCY_MAX_BUCKET = 148u * 256u;  // one 256-point chunk per SM of a B200: the fused kernel's reach
-uint32_t chunk_size_for(uint32_t n, bool throughput, uint32_t big = 1920u) {
+uint32_t chunk_size_for(uint32_t n, bool throughput, uint32_t big = 3840u) {
     if (throughput) return n <= 2048u ? 256u : big;
     return n <= LATENCY_MAX_BUCKET ? 256u : big;
 }
@@ -569,7 +569,7 @@ static int stage_impl(lk_handle h, int batch, const lk_state* x, const double* P
         }
     }
     // 60 groups split evenly over the pipelined kernel's 6 warps
-    const uint32_t big_chunk = 1920u;
+    const uint32_t big_chunk = 3840u;
     auto build_tables = [&](bool throughput, std::vector<ChunkDesc>& chunks, std::vector<StepInit>& inits) {
         chunks.clear();
         inits.assign((size_t)max_buckets * batch, StepInit());

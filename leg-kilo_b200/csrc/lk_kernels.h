@@ -48,7 +48,7 @@ struct ResidualArgs {
     uint32_t* fb_cnt;   // [total_chunks][S2_FB_WARPS]
     Globals g;
 };
-constexpr uint32_t S2_FB_WARPS = 6, S2_FB_CAP = 352;
+constexpr uint32_t S2_FB_WARPS = 6, S2_FB_CAP = 704;
 
 // single: every chunk of the launch holds at most 256 points (one point per thread, one pass); otherwise blocks make
 // several passes over their chunk

@@ -24,7 +24,7 @@ namespace lk {
 
 namespace {
 
-constexpr int S2_MAXPTS = 2048;  // largest chunk lk_api.cu hands out
+constexpr int S2_MAXPTS = 4096;  // largest chunk lk_api.cu hands out (3 840 = 6 warps x 20 groups)
 // slot of a lane: the 144 used bytes of the plane's hot image (lk_device.cuh: HotRec) | root index at 144 | point at 160.
 // 176-byte stride = 11 x 16 B: the 128-bit reads of 8 consecutive lanes fall into 8 disjoint groups of 4 banks.
 constexpr int S2_STRIDE = 176, S2_SLOT_ROOT = 144, S2_SLOT_PT = 160, S2_REC_PIECES = 9;

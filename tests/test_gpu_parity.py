@@ -93,7 +93,7 @@ def test_single_scan_paths_agree_with_oracle(fused):
 
 
 def test_throughput_family_chunk_edges():
-    """Calls with >= 2 scans take the throughput family: 1 920- / 256-point chunks, warps streaming 32-point groups
+    """Calls with >= 2 scans take the throughput family: 3 840- / 256-point chunks, warps streaming 32-point groups
     through a software pipeline. Scan lengths sit on every edge of that machinery (one point, group and chunk
     boundaries +-1, several chunks, a warp without work); the kernel must reproduce the oracle's residual counts
     exactly and its state / covariance within tolerance, whatever mixture of lengths shares the call."""
