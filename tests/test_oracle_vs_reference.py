@@ -371,3 +371,18 @@ def test_random_streaming_frames_match(seed, kin, cfg_name, voxel, sigma):
     np.testing.assert_allclose(ro["world"], out["world"], rtol=0, atol=3e-6)
     _same_filter(o, r, x0, tol=1e-8)
     mapcmp.compare_blobs(r.map_export(), o.map_export(), rtol=1e-5, pt_atol=1e-10, var_rtol=1e-7)
+
+
+def test_state_boxminus_matches_including_small_angles():
+    """State::operator- (eskf.cc:31-45) with Log (math_utils.hpp:71-76): the trace > 3 - 1e-6 and |theta| < 1e-3 branches included."""
+    g = np.random.default_rng(11)
+    for scale in (1.0, 1e-2, 5e-4, 1e-4, 1e-7, 0.0):
+        for _ in range(6):
+            a, b = abi.default_states(1), abi.default_states(1)
+            Ra = synth.exp_so3(g.standard_normal(3))
+            a["rot"][0] = Ra.ravel()
+            b["rot"][0] = (Ra @ synth.exp_so3(scale * g.standard_normal(3))).ravel()
+            for f in ("pos", "vel", "ba", "bw", "grav", "imu_a", "imu_w", "bv", "contact"):
+                a[f][0] = g.standard_normal(3); b[f][0] = g.standard_normal(3)
+            do, dr = lko.boxminus(b, a), lkref.boxminus(b, a)
+            np.testing.assert_allclose(do, dr, rtol=0, atol=1e-15 + 1e-13 * np.abs(dr).max())
