@@ -87,3 +87,41 @@ def test_two_rank_gloo_sharding(tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
                           "127.0.0.1", "--master-port", "29541", str(w), pkg], capture_output=True, text=True, timeout=240, env=env)
     assert "GLOO_OK 2" in out.stdout, out.stdout + out.stderr
+
+
+def test_bench_clock_sampler_windows_and_traffic_lookup():
+    """bench.py's host-side bookkeeping: clock samples are taken from the timed region, or — when that is shorter than the sampling
+    period — from the last samples before its end; throttle reasons are collected; the throughput family's traffic is the sum of its two
+    committed ncu captures."""
+    import time
+
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class FakeProc:
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+        def kill(self): pass
+
+    now = time.time()
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    s.rows = [(now - 1.0, "210, 1965, Not Active, Not Active, Not Active, Not Active"),      # idle, long before
+              (now - 0.5, "1965, 1965, Not Active, Not Active, Not Active, Not Active"),    # warm-up
+              (now - 0.01, "1950, 1965, Not Active, Not Active, Not Active, Active")]       # inside the region
+    s.t_begin = now - 0.02
+    out = s.stop()
+    assert out["window"] == "timed region" and out["samples"] == 1 and out["sm_mhz"] == 1950.0 and out["reasons"] == ["sw_power_cap"]
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    s.rows = [(now - 1.0, "210, 1965, Not Active, Not Active, Not Active, Not Active"),
+              (now - 0.5, "1965, 1965, Not Active, Not Active, Not Active, Not Active")]
+    s.t_begin = time.time()  # a region with no sample of its own
+    out = s.stop()
+    assert out["window"].startswith("last samples") and out["samples"] == 2 and out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0
+    total, note = bench.ncu_traffic_family()
+    a, _ = bench.ncu_traffic("k_residual_stream2")
+    b, _ = bench.ncu_traffic("k_residual_fallback")
+    assert total == a + b and "k_residual_fallback" in note
+    assert bench.ncu_traffic("k_scan_fused")[0] > 1e6
